@@ -1,0 +1,187 @@
+/*
+ * larvanet_b200 -- C-ABI of the B200-native (sm_100a) LarvaNet / LarvaNetV2 / EDSR-baseline x4 SR hot path.
+ *
+ * The reference (Geunwoo-Jeon/LarvaNet) is pure Python/PyTorch and has NO FFI of its own:
+ * every entry point below replaces one or more `torch.nn` call sites inside the reference's modules; the
+ * reference interface each one replaces is cited as file:line relative to the reference root.  Python binds
+ * these with ctypes (`larvanet_b200/_lib.py`; stub shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless a parameter says "host"; the library never allocates, frees or
+ *     synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 = ok, otherwise an LV_ERR_* code; lv_last_error() returns a thread-local message.
+ *   - activations are NHWC.  dtype LV_BF16 is the product path (tcgen05 tensor cores, fp32 accumulate);
+ *     dtype LV_F32 is the fp32 validation mode (CUDA-core direct convolution, same epilogues).
+ *   - images at the Python boundary stay NCHW fp32 on the 0..255 scale like the reference
+ *     (models/LarvaNet.py:163-171).
+ */
+#ifndef LARVANET_B200_H_
+#define LARVANET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LV_ABI_VERSION 1
+
+enum { LV_F32 = 0, LV_BF16 = 1 };
+
+enum {
+  LV_OK = 0,
+  LV_ERR_INVALID = 1,     /* bad argument / unsupported shape */
+  LV_ERR_CUDA = 2,        /* a CUDA runtime call failed (message has the cudaError string) */
+  LV_ERR_UNSUPPORTED = 3  /* wrong device (needs sm_100) */
+};
+
+/* conv epilogue kinds */
+enum {
+  LV_EPI_NHWC = 0,      /* out[n,h,w,co]                       (ResidualBlock / merge / EDSR body convs)   */
+  LV_EPI_PS4_NCHW = 1,  /* out_hr[n,c,4h+i,4w+j] = v[16c+4i+j] + base   (LarvaLeg / LarvaTail, fp32 NCHW)  */
+  LV_EPI_PS2_NHWC = 2,  /* out[n,2h+i,2w+j,c]    = v[4c+2i+j]           (EDSR UpsampleBlock, NHWC)          */
+  LV_EPI_RGB_NCHW = 3   /* out_hr[n,c,h,w] = post_w[c,:].v[0:3] + post_b[c]   (EDSR final_conv + 1x1)      */
+};
+
+#define LV_MAX_SRC 4
+
+/*
+ * One 3x3 / stride 1 / pad 1 convolution with a fused epilogue:
+ *     v = res_scale * (conv(src..) + bias);  if (relu) v = max(v,0);  if (mask) v = mask>0 ? v : 0;
+ *     v += res1;  v += res2;   then the epilogue kind decides how v is stored.
+ * Replaces nn.Conv2d + nn.ReLU + torch.add + nn.PixelShuffle + `out += base` + nn.L1Loss at
+ *   models/LarvaNet.py:209-220 (ResidualBlock), :246-248 (LarvaBody skip), :255-267 (LarvaLeg),
+ *   models/LarvaNetV2.py:318-334 (LarvaTail; `src[0..num_src)` replaces torch.cat + merge_conv),
+ *   models/edsr.py:139-153,156-173,182-207, and -- with flipped/transposed weights, `mask` and `res*` --
+ *   the autograd conv backward-data of the same layers (loss.backward(), models/LarvaNet.py:113).
+ */
+typedef struct lv_conv_args {
+  int32_t n, h, w;           /* conv grid (input == output resolution)                                   */
+  int32_t cin;               /* channels per source; tensor-core path needs cin % 16 == 0                 */
+  int32_t num_src;           /* 1..LV_MAX_SRC                                                            */
+  int32_t cout;              /* real output channels                                                      */
+  int32_t dtype;             /* LV_BF16 | LV_F32 : type of src/out/res/mask/grad_sign                     */
+  int32_t relu;
+  int32_t epilogue;          /* LV_EPI_*                                                                  */
+  int32_t reserved0;
+  float res_scale;           /* 1.0 unless EDSR --edsr_res_weight                                        */
+  float reserved1;
+  const void* src[LV_MAX_SRC]; /* NHWC [n,h,w,cin]                                                        */
+  const void* weights;       /* packed by lv_pack_conv3x3_weights for this dtype                          */
+  const float* bias;         /* [cout] or NULL                                                            */
+  const void* mask;          /* NHWC [n,h,w,cout] or NULL                                                 */
+  const void* res1;          /* NHWC [n,h,w,cout] or NULL                                                 */
+  const void* res2;          /* NHWC [n,h,w,cout] or NULL                                                 */
+  void* out;                 /* EPI_NHWC: [n,h,w,cout]; EPI_PS2_NHWC: [n,2h,2w,cout/4]; else unused       */
+  float* out_hr;             /* EPI_PS4_NCHW: fp32 [n,cout/16,4h,4w] (NULL = skip store); EPI_RGB: [n,3,h,w] */
+  const float* base_hr;      /* EPI_PS4_NCHW: fp32 [n,cout/16,4h,4w] added to the shuffled output, or NULL */
+  const float* truth_hr;     /* EPI_PS4_NCHW: if non-NULL, fuse nn.L1Loss: loss_sum += sum|out-truth| and   */
+  double* loss_sum;          /*   write grad_sign = sign(out-truth) in the pre-shuffle NHWC layout          */
+  void* grad_sign;           /* NHWC [n,h,w,cout] of dtype                                                 */
+  const float* post_w;       /* EPI_RGB_NCHW: fp32 [3,3] 1x1 conv weight (row-major [out,in]) or NULL      */
+  const float* post_b;       /* EPI_RGB_NCHW: fp32 [3] or NULL                                             */
+} lv_conv_args;
+
+/* Weight-gradient work item (one conv layer, or one source slice of the V2 merge conv). */
+typedef struct lv_wgrad_item {
+  int32_t n, h, w;
+  int32_t cin, cout;         /* cin of THIS slice (tensor-core path: 48 or 64), cout <= 64 on the tc path  */
+  int32_t cin_total, cin_off;/* dw is [cout, cin_total, 3, 3]; this item fills ci in [cin_off, cin_off+cin) */
+  int32_t dtype;
+  const void* x;             /* NHWC [n,h,w,cin]  layer input saved by the forward pass                    */
+  const void* dy;            /* NHWC [n,h,w,cout] gradient wrt the conv output (before bias)               */
+  float* dw;                 /* fp32 OIHW, ACCUMULATED INTO (dw += scale * sum)                            */
+  float* db;                 /* fp32 [cout], accumulated into; NULL to skip                                */
+  float scale;
+  int32_t reserved;
+} lv_wgrad_item;
+
+/* Weight re-pack work item: fp32 OIHW master weight [O, I, 3, 3] -> packed operand for lv_conv3x3.
+ *   transpose = 0 (forward operand):        packed conv has cout = O and cin_total = i_cnt, reading the input-channel
+ *                                            slice [i_off, i_off+i_cnt) of the master weight.
+ *   transpose = 1 (backward-data operand):  taps rotated by 180 degrees, in/out swapped: packed conv has cout = i_cnt
+ *                                            (the slice of ORIGINAL input channels it produces gradients for) and
+ *                                            cin_total = O.
+ *   `cin` = channels per source of the packed conv (cin_total must be a multiple of it). */
+typedef struct lv_pack_item {
+  const float* w;
+  void* packed;              /* output, lv_packed_weight_bytes(packed cout, packed cin_total, dtype) bytes          */
+  int32_t O, I;
+  int32_t transpose;
+  int32_t i_off, i_cnt;
+  int32_t cin;
+  int32_t dtype;
+  int32_t reserved;
+} lv_pack_item;
+
+const char* lv_last_error(void);
+int lv_abi_version(void);
+/* 0 if device `dev` can run the library (compute capability 10.x); fills sm_count if non-NULL */
+int lv_device_check(int dev, int* sm_count);
+
+/* bytes of the packed weight for a conv with `cout` outputs and `cin_total` inputs */
+int64_t lv_packed_weight_bytes(int cout, int cin_total, int dtype);
+/* batched pack: `items` is a HOST array (copied by value into the launch); count <= 64 per call */
+int lv_pack_conv3x3_weights(const lv_pack_item* items, int count, void* stream);
+
+/* the conv (see lv_conv_args).  `max_ctas` <= 0 lets the library choose (persistent grid).
+ * LV_BF16 -> tcgen05 tensor-core kernel; LV_F32 -> fp32 validation kernel.  There is no CPU fallback. */
+int lv_conv3x3(const lv_conv_args* args, int max_ctas, void* stream);
+/* TEST-ONLY cross-check: the same conv on CUDA cores for either dtype (bf16: identical operands, fp32 accumulate) */
+int lv_conv3x3_simt(const lv_conv_args* args, void* stream);
+
+/*
+ * LarvaHead conv (3->cout, fp32 math) fused with the bicubic x4 base.
+ * Replaces models/LarvaNet.py:227,231-233 (LarvaHead) and :283-285 (F.interpolate bicubic, align_corners=False);
+ * for EDSR (`pre_w`/`pre_b` non-NULL) also the 1x1 MeanShift before first_conv (models/edsr.py:197-198).
+ *   x: fp32 NCHW [n,3,h,w];  fea: NHWC [n,h,w,cout] of dtype;  base_hr: fp32 NCHW [n,3,4h,4w] or NULL
+ */
+int lv_head_bicubic_fwd(const float* x, const float* w, const float* b, const float* pre_w, const float* pre_b,
+                        void* fea, float* base_hr, int n, int h, int w_, int cout, int dtype, void* stream);
+/* bicubic x4 only (LarvaNetModule.base, models/LarvaNet.py:283-285) */
+int lv_bicubic_x4(const float* x, float* base_hr, int n, int c, int h, int w_, void* stream);
+/* head weight/bias gradient: dw[cout,3,3,3] += scale*sum_px dy*x, db += scale*sum dy (autograd of :227) */
+int lv_head_wgrad(const float* x, const void* dy, float* dw, float* db, int n, int h, int w_, int cout,
+                  int dtype, float scale, void* stream);
+
+/*
+ * Batched weight gradients.  `items_dev` is a DEVICE array of `count` items (same dtype; bf16 needs cin == 48);
+ * `items_host` is the same array on the host (used for validation and launch geometry only).  Each item is
+ * split over `splits` CTAs along its pixel tiles.
+ * `workspace` holds split-K partials: lv_wgrad_workspace_bytes(...) bytes.  Replaces autograd's conv
+ * backward-filter + bias reduction for every Conv2d(48|64 -> <=64) of the path.
+ */
+int64_t lv_wgrad_workspace_bytes(const lv_wgrad_item* items_host, int count, int splits);
+int lv_conv3x3_wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int count, int splits,
+                     void* workspace, void* stream);
+/* TEST-ONLY cross-check of the tensor-core wgrad on CUDA cores (either dtype; fp32 atomics) */
+int lv_conv3x3_wgrad_simt(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int count, int splits,
+                          void* stream);
+
+/* layout / dtype helpers at the module boundary (NCHW fp32 <-> NHWC dtype) */
+int lv_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w_, int dtype, void* stream);
+int lv_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w_, int dtype, void* stream);
+
+/*
+ * Stand-alone L1 loss + gradient on fp32 NCHW HR images (nn.L1Loss, models/LarvaNet.py:85,108):
+ *   loss_sum += sum|out-truth|;  if grad_sign: sign(out-truth) un-shuffled (PixelShuffle(4) backward) to
+ *   NHWC [n,h,w,16*c] of dtype.
+ */
+int lv_l1_loss_grad(const float* out_hr, const float* truth_hr, double* loss_sum, void* grad_sign,
+                    int n, int c, int h, int w_, int dtype, void* stream);
+
+/*
+ * Fused multi-tensor AdamW over a flat fp32 parameter/gradient arena (torch.optim.AdamW defaults,
+ * models/LarvaNet.py:86-88,114).  `grad_scale` multiplies the gradient first (DP mean / loss scaling).
+ */
+int lv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  void* stream);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t lv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LARVANET_B200_H_ */

@@ -1,0 +1,186 @@
+// extern "C" boundary of liblarvanet_b200.so (declared in include/larvanet_b200.h).
+// Plain pointers and sizes only; no torch types.  Every entry validates its arguments, enqueues on the caller's stream
+// and returns an LV_* status; failures leave a thread-local message for lv_last_error().
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "lv_common.cuh"
+
+namespace lv {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+// implemented in the other translation units
+int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
+int conv3x3_simt(const lv_conv_args& a, cudaStream_t stream);
+int pick_ntile(int cout_pad);
+int head_bicubic_fwd(const float*, const float*, const float*, const float*, const float*, void*, float*, int, int, int, int,
+                     int, cudaStream_t);
+int bicubic_x4(const float*, float*, int, int, int, int, cudaStream_t);
+int head_wgrad(const float*, const void*, float*, float*, int, int, int, int, int, float, cudaStream_t);
+int pack_weights(const lv_pack_item*, int, cudaStream_t);
+int nchw_to_nhwc(const float*, void*, int, int, int, int, int, cudaStream_t);
+int nhwc_to_nchw(const void*, float*, int, int, int, int, int, cudaStream_t);
+int l1_loss_grad(const float*, const float*, double*, void*, int, int, int, int, int, cudaStream_t);
+int adamw_step(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
+long long wgrad_workspace_bytes(const lv_wgrad_item*, int, int);
+int wgrad(const lv_wgrad_item*, const lv_wgrad_item*, int, int, void*, cudaStream_t);
+int wgrad_simt(const lv_wgrad_item*, const lv_wgrad_item*, int, int, cudaStream_t);
+
+static int check_conv(const lv_conv_args* a) {
+  LV_CHECK_ARG(a != nullptr, "conv3x3: null args");
+  LV_CHECK_ARG(a->n >= 0 && a->h >= 0 && a->w >= 0, "conv3x3: negative geometry");
+  LV_CHECK_ARG(a->dtype == LV_F32 || a->dtype == LV_BF16, "conv3x3: bad dtype %d", a->dtype);
+  LV_CHECK_ARG(a->num_src >= 1 && a->num_src <= LV_MAX_SRC, "conv3x3: num_src must be 1..%d", LV_MAX_SRC);
+  LV_CHECK_ARG(a->cin > 0 && a->cout > 0, "conv3x3: bad channel counts");
+  LV_CHECK_ARG(a->weights != nullptr, "conv3x3: null weights");
+  for (int s = 0; s < a->num_src; ++s) LV_CHECK_ARG(a->src[s] != nullptr, "conv3x3: null source %d", s);
+  switch (a->epilogue) {
+    case LV_EPI_NHWC:
+      LV_CHECK_ARG(a->out != nullptr, "conv3x3: EPI_NHWC needs out");
+      LV_CHECK_ARG(a->cout % 16 == 0, "conv3x3: EPI_NHWC needs cout %% 16 == 0 (got %d)", a->cout);
+      break;
+    case LV_EPI_PS4_NCHW:
+      LV_CHECK_ARG(a->cout % 16 == 0, "conv3x3: EPI_PS4 needs cout %% 16 == 0");
+      LV_CHECK_ARG(a->out_hr != nullptr || a->truth_hr != nullptr, "conv3x3: EPI_PS4 needs out_hr and/or truth_hr");
+      LV_CHECK_ARG(a->truth_hr == nullptr || a->loss_sum != nullptr, "conv3x3: truth_hr given without loss_sum");
+      break;
+    case LV_EPI_PS2_NHWC:
+      LV_CHECK_ARG(a->out != nullptr && a->cout % 16 == 0, "conv3x3: EPI_PS2 needs out and cout %% 16 == 0");
+      break;
+    case LV_EPI_RGB_NCHW:
+      LV_CHECK_ARG(a->out_hr != nullptr && a->cout == 3, "conv3x3: EPI_RGB needs out_hr and cout == 3");
+      LV_CHECK_ARG(a->mask == nullptr && a->res1 == nullptr && a->res2 == nullptr, "conv3x3: EPI_RGB takes no mask/residual");
+      break;
+    default:
+      LV_CHECK_ARG(false, "conv3x3: unknown epilogue %d", a->epilogue);
+  }
+  return LV_OK;
+}
+
+}  // namespace lv
+
+using namespace lv;
+
+extern "C" {
+
+const char* lv_last_error(void) { return g_err; }
+int lv_abi_version(void) { return LV_ABI_VERSION; }
+int64_t lv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int lv_device_check(int dev, int* sm) {
+  cudaDeviceProp prop;
+  LV_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (sm != nullptr) *sm = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; larvanet_b200 is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    return LV_ERR_UNSUPPORTED;
+  }
+  return LV_OK;
+}
+
+int64_t lv_packed_weight_bytes(int cout, int cin_total, int dtype) {
+  const int64_t cout_pad = (cout + 15) / 16 * 16;
+  return cout_pad * cin_total * 9 * (dtype == LV_BF16 ? 2 : 4);
+}
+
+int lv_pack_conv3x3_weights(const lv_pack_item* items, int count, void* stream) {
+  LV_CHECK_ARG(items != nullptr || count == 0, "pack: null items");
+  return pack_weights(items, count, static_cast<cudaStream_t>(stream));
+}
+
+int lv_conv3x3(const lv_conv_args* a, int max_ctas, void* stream) {
+  int rc = check_conv(a);
+  if (rc != LV_OK) return rc;
+  if (a->dtype == LV_BF16) {
+    LV_CHECK_ARG(a->cin % 16 == 0, "conv3x3: the tensor-core path needs cin %% 16 == 0 (got %d)", a->cin);
+    return conv3x3_tc(*a, max_ctas, static_cast<cudaStream_t>(stream));
+  }
+  return conv3x3_simt(*a, static_cast<cudaStream_t>(stream));
+}
+
+int lv_conv3x3_simt(const lv_conv_args* a, void* stream) {
+  int rc = check_conv(a);
+  if (rc != LV_OK) return rc;
+  return conv3x3_simt(*a, static_cast<cudaStream_t>(stream));
+}
+
+int lv_head_bicubic_fwd(const float* x, const float* w, const float* b, const float* pre_w, const float* pre_b, void* fea,
+                        float* base_hr, int n, int h, int w_, int cout, int dtype, void* stream) {
+  LV_CHECK_ARG(x && w && fea, "head: null pointer");
+  LV_CHECK_ARG((pre_w == nullptr) == (pre_b == nullptr), "head: pre_w and pre_b go together");
+  return head_bicubic_fwd(x, w, b, pre_w, pre_b, fea, base_hr, n, h, w_, cout, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int lv_bicubic_x4(const float* x, float* base_hr, int n, int c, int h, int w_, void* stream) {
+  LV_CHECK_ARG(x && base_hr, "bicubic: null pointer");
+  return bicubic_x4(x, base_hr, n, c, h, w_, static_cast<cudaStream_t>(stream));
+}
+
+int lv_head_wgrad(const float* x, const void* dy, float* dw, float* db, int n, int h, int w_, int cout, int dtype,
+                  float scale, void* stream) {
+  LV_CHECK_ARG(x && dy && dw, "head wgrad: null pointer");
+  return head_wgrad(x, dy, dw, db, n, h, w_, cout, dtype, scale, static_cast<cudaStream_t>(stream));
+}
+
+int64_t lv_wgrad_workspace_bytes(const lv_wgrad_item* items_host, int count, int splits) {
+  return wgrad_workspace_bytes(items_host, count, splits);
+}
+
+int lv_conv3x3_wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int count, int splits, void* workspace,
+                     void* stream) {
+  LV_CHECK_ARG(items_host && items_dev, "wgrad: null item arrays");
+  return wgrad(items_host, items_dev, count, splits, workspace, static_cast<cudaStream_t>(stream));
+}
+
+int lv_conv3x3_wgrad_simt(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int count, int splits,
+                          void* stream) {
+  LV_CHECK_ARG(items_host && items_dev, "wgrad: null item arrays");
+  return wgrad_simt(items_host, items_dev, count, splits, static_cast<cudaStream_t>(stream));
+}
+
+int lv_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w_, int dtype, void* stream) {
+  LV_CHECK_ARG(src && dst, "nchw_to_nhwc: null pointer");
+  return nchw_to_nhwc(src, dst, n, c, h, w_, dtype, static_cast<cudaStream_t>(stream));
+}
+int lv_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w_, int dtype, void* stream) {
+  LV_CHECK_ARG(src && dst, "nhwc_to_nchw: null pointer");
+  return nhwc_to_nchw(src, dst, n, c, h, w_, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int lv_l1_loss_grad(const float* out_hr, const float* truth_hr, double* loss_sum, void* grad_sign, int n, int c, int h,
+                    int w_, int dtype, void* stream) {
+  LV_CHECK_ARG(out_hr && truth_hr, "l1: null pointer");
+  return l1_loss_grad(out_hr, truth_hr, loss_sum, grad_sign, n, c, h, w_, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int lv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  LV_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adamw: null pointer");
+  return adamw_step(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                    static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+// LarvaHead conv (3 -> cout, K = 27, fp32 math on CUDA cores: 0.18 % of the MACs, HBM-bound) fused with the
+// bicubic x4 base image -- both read the same LR tile -- plus the head weight gradient.
+//
+// Bicubic restates ATen upsample_bicubic2d for scale_factor=4, align_corners=False (reference
+// models/LarvaNet.py:283-285): src = (d+0.5)/4-0.5, taps floor-1..floor+2, Keys cubic A=-0.75, indices clamped.
+// Output row 4y+i uses t = {0.625, 0.875, 0.125, 0.375}[i] and first tap row y + {-2,-2,-1,-1}[i].
+#include "lv_common.cuh"
+
+namespace lv {
+
+constexpr int kHT = 16;            // LR tile edge
+constexpr int kHH = kHT + 4;       // +-2 halo for bicubic (conv uses +-1 of it)
+
+__device__ __forceinline__ void cubic_coeffs(float t, float* c) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kHT* kHT)
+head_bicubic_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                    const float* __restrict__ pre_w, const float* __restrict__ pre_b, T* __restrict__ fea,
+                    float* __restrict__ base_hr, int N, int H, int W, int cout) {
+  __shared__ float sx[3][kHH][kHH + 1];   // index-clamped LR tile (what bicubic reads)
+  __shared__ float sc[3][kHT + 2][kHT + 3];  // conv input: optional 1x1 pre-conv, ZERO outside the image
+  extern __shared__ float sw[];           // [27][cout] transposed weights, then [cout] bias
+  const int tx = threadIdx.x % kHT, ty = threadIdx.x / kHT;
+  const int x0 = blockIdx.x * kHT, y0 = blockIdx.y * kHT, n = blockIdx.z;
+
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
+    const int k = i / cout, co = i % cout;   // k = c*9 + ky*3 + kx  (OIHW inner order)
+    sw[i] = w[co * 27 + k];
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) sw[27 * cout + i] = (b != nullptr) ? b[i] : 0.f;
+  for (int i = threadIdx.x; i < 3 * kHH * kHH; i += blockDim.x) {
+    const int c = i / (kHH * kHH), r = (i / kHH) % kHH, q = i % kHH;
+    const int gy = min(max(y0 - 2 + r, 0), H - 1), gx = min(max(x0 - 2 + q, 0), W - 1);
+    sx[c][r][q] = x[((static_cast<size_t>(n) * 3 + c) * H + gy) * W + gx];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (kHT + 2) * (kHT + 2); i += blockDim.x) {
+    const int r = i / (kHT + 2), q = i % (kHT + 2);
+    const int gy = y0 - 1 + r, gx = x0 - 1 + q;
+    const bool inb = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    float v0 = sx[0][r + 1][q + 1], v1 = sx[1][r + 1][q + 1], v2 = sx[2][r + 1][q + 1];
+    if (pre_w != nullptr) {  // EDSR mean_shift: general 1x1 conv (models/edsr.py:129-136,197)
+      const float u0 = pre_w[0] * v0 + pre_w[1] * v1 + pre_w[2] * v2 + pre_b[0];
+      const float u1 = pre_w[3] * v0 + pre_w[4] * v1 + pre_w[5] * v2 + pre_b[1];
+      const float u2 = pre_w[6] * v0 + pre_w[7] * v1 + pre_w[8] * v2 + pre_b[2];
+      v0 = u0; v1 = u1; v2 = u2;
+    }
+    sc[0][r][q] = inb ? v0 : 0.f;
+    sc[1][r][q] = inb ? v1 : 0.f;
+    sc[2][r][q] = inb ? v2 : 0.f;
+  }
+  __syncthreads();
+
+  const int gy = y0 + ty, gx = x0 + tx;
+  if (gy >= H || gx >= W) return;
+
+  // ---- conv 3 -> cout ----
+  float in[27];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) in[c * 9 + ky * 3 + kx] = sc[c][ty + ky][tx + kx];
+  T* fp = fea + ((static_cast<size_t>(n) * H + gy) * W + gx) * cout;
+  for (int co0 = 0; co0 < cout; co0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = sw[27 * cout + co0 + i];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(in[k], sw[k * cout + co0 + i], acc[i]);
+    }
+    store16(fp + co0, acc);
+  }
+
+  // ---- bicubic x4 base ----
+  if (base_hr == nullptr) return;
+  const float tph[4] = {0.625f, 0.875f, 0.125f, 0.375f};
+  const int first[4] = {-2, -2, -1, -1};
+  float cw[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cubic_coeffs(tph[i], cw[i]);
+  const size_t W4 = static_cast<size_t>(W) * 4, H4 = static_cast<size_t>(H) * 4;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    // horizontal pass on the 5 LR rows y-2..y+2 -> hz[row][j]
+    float hz[5][4];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* p = &sx[c][ty + r][tx + 2 + first[j]];
+        hz[r][j] = p[0] * cw[j][0] + p[1] * cw[j][1] + p[2] * cw[j][2] + p[3] * cw[j][3];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r0 = first[i] + 2;
+      float4 o;
+      o.x = hz[r0][0] * cw[i][0] + hz[r0 + 1][0] * cw[i][1] + hz[r0 + 2][0] * cw[i][2] + hz[r0 + 3][0] * cw[i][3];
+      o.y = hz[r0][1] * cw[i][0] + hz[r0 + 1][1] * cw[i][1] + hz[r0 + 2][1] * cw[i][2] + hz[r0 + 3][1] * cw[i][3];
+      o.z = hz[r0][2] * cw[i][0] + hz[r0 + 1][2] * cw[i][1] + hz[r0 + 2][2] * cw[i][2] + hz[r0 + 3][2] * cw[i][3];
+      o.w = hz[r0][3] * cw[i][0] + hz[r0 + 1][3] * cw[i][1] + hz[r0 + 2][3] * cw[i][2] + hz[r0 + 3][3] * cw[i][3];
+      *reinterpret_cast<float4*>(base_hr + ((static_cast<size_t>(n) * 3 + c) * H4 + (4 * gy + i)) * W4 + 4 * gx) = o;
+    }
+  }
+}
+
+// bicubic only, any channel count (LarvaNetModule.base on its own)
+__global__ void __launch_bounds__(kHT* kHT)
+bicubic_kernel(const float* __restrict__ x, float* __restrict__ base_hr, int NC, int H, int W) {
+  __shared__ float sx[kHH][kHH + 1];
+  const int tx = threadIdx.x % kHT, ty = threadIdx.x / kHT;
+  const int x0 = blockIdx.x * kHT, y0 = blockIdx.y * kHT, nc = blockIdx.z;
+  for (int i = threadIdx.x; i < kHH * kHH; i += blockDim.x) {
+    const int r = i / kHH, q = i % kHH;
+    const int gy = min(max(y0 - 2 + r, 0), H - 1), gx = min(max(x0 - 2 + q, 0), W - 1);
+    sx[r][q] = x[(static_cast<size_t>(nc) * H + gy) * W + gx];
+  }
+  __syncthreads();
+  const int gy = y0 + ty, gx = x0 + tx;
+  if (gy >= H || gx >= W) return;
+  const float tph[4] = {0.625f, 0.875f, 0.125f, 0.375f};
+  const int first[4] = {-2, -2, -1, -1};
+  float cw[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) cubic_coeffs(tph[i], cw[i]);
+  float hz[5][4];
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* p = &sx[ty + r][tx + 2 + first[j]];
+      hz[r][j] = p[0] * cw[j][0] + p[1] * cw[j][1] + p[2] * cw[j][2] + p[3] * cw[j][3];
+    }
+  const size_t W4 = static_cast<size_t>(W) * 4, H4 = static_cast<size_t>(H) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r0 = first[i] + 2;
+    float4 o;
+    o.x = hz[r0][0] * cw[i][0] + hz[r0 + 1][0] * cw[i][1] + hz[r0 + 2][0] * cw[i][2] + hz[r0 + 3][0] * cw[i][3];
+    o.y = hz[r0][1] * cw[i][0] + hz[r0 + 1][1] * cw[i][1] + hz[r0 + 2][1] * cw[i][2] + hz[r0 + 3][1] * cw[i][3];
+    o.z = hz[r0][2] * cw[i][0] + hz[r0 + 1][2] * cw[i][1] + hz[r0 + 2][2] * cw[i][2] + hz[r0 + 3][2] * cw[i][3];
+    o.w = hz[r0][3] * cw[i][0] + hz[r0 + 1][3] * cw[i][1] + hz[r0 + 2][3] * cw[i][2] + hz[r0 + 3][3] * cw[i][3];
+    *reinterpret_cast<float4*>(base_hr + (static_cast<size_t>(nc) * H4 + (4 * gy + i)) * W4 + 4 * gx) = o;
+  }
+}
+
+// head weight gradient: dw[co][c][ky][kx] += scale * sum_px dy[px][co] * x[c][y+ky-1][x+kx-1];  db[co] += scale * sum dy
+constexpr int kGW = 16, kGH = 8;  // pixel tile of the head wgrad
+template <typename T>
+__global__ void __launch_bounds__(256)
+head_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db,
+                  int N, int H, int W, int cout, float scale) {
+  __shared__ float sx[3][kGH + 2][kGW + 2];
+  extern __shared__ float sdy[];  // [kGH*kGW][cout+1]
+  const int cp = cout + 1;
+  const int x0 = blockIdx.x * kGW, y0 = blockIdx.y * kGH, n = blockIdx.z;
+  for (int i = threadIdx.x; i < 3 * (kGH + 2) * (kGW + 2); i += 256) {
+    const int c = i / ((kGH + 2) * (kGW + 2)), r = (i / (kGW + 2)) % (kGH + 2), q = i % (kGW + 2);
+    const int gy = y0 - 1 + r, gx = x0 - 1 + q;
+    sx[c][r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((static_cast<size_t>(n) * 3 + c) * H + gy) * W + gx] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kGH * kGW * cout; i += 256) {
+    const int p = i / cout, co = i % cout;
+    const int gy = y0 + p / kGW, gx = x0 + p % kGW;
+    sdy[p * cp + co] = (gy < H && gx < W) ? to_f32(dy[((static_cast<size_t>(n) * H + gy) * W + gx) * cout + co]) : 0.f;
+  }
+  __syncthreads();
+  const int nout = 28 * cout;  // 27 weight taps + 1 bias row per output channel
+  for (int o = threadIdx.x; o < nout; o += 256) {
+    const int k = o / cout, co = o % cout;
+    float acc = 0.f;
+    if (k < 27) {
+      const int c = k / 9, ky = (k / 3) % 3, kx = k % 3;
+      for (int p = 0; p < kGH * kGW; ++p) acc = fmaf(sdy[p * cp + co], sx[c][p / kGW + ky][p % kGW + kx], acc);
+      atomicAdd(dw + co * 27 + k, scale * acc);
+    } else if (db != nullptr) {
+      for (int p = 0; p < kGH * kGW; ++p) acc += sdy[p * cp + co];
+      atomicAdd(db + co, scale * acc);
+    }
+  }
+}
+
+int head_bicubic_fwd(const float* x, const float* w, const float* b, const float* pre_w, const float* pre_b, void* fea,
+                     float* base_hr, int n, int h, int w_, int cout, int dtype, cudaStream_t stream) {
+  if (n == 0 || h == 0 || w_ == 0) return LV_OK;
+  LV_CHECK_ARG(cout % 16 == 0 && cout <= 256, "head conv: cout must be a multiple of 16 (got %d)", cout);
+  LV_CHECK_ARG(n <= 65535, "head conv: batch too large for one launch");
+  dim3 grid((w_ + kHT - 1) / kHT, (h + kHT - 1) / kHT, n);
+  const size_t smem = static_cast<size_t>(28) * cout * sizeof(float);
+  if (dtype == LV_F32)
+    head_bicubic_kernel<float><<<grid, kHT * kHT, smem, stream>>>(x, w, b, pre_w, pre_b, static_cast<float*>(fea), base_hr,
+                                                                 n, h, w_, cout);
+  else
+    head_bicubic_kernel<__nv_bfloat16><<<grid, kHT * kHT, smem, stream>>>(
+        x, w, b, pre_w, pre_b, static_cast<__nv_bfloat16*>(fea), base_hr, n, h, w_, cout);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+int bicubic_x4(const float* x, float* base_hr, int n, int c, int h, int w_, cudaStream_t stream) {
+  if (n * c == 0 || h == 0 || w_ == 0) return LV_OK;
+  LV_CHECK_ARG(static_cast<long long>(n) * c <= 65535, "bicubic: n*c too large for one launch");
+  dim3 grid((w_ + kHT - 1) / kHT, (h + kHT - 1) / kHT, n * c);
+  bicubic_kernel<<<grid, kHT * kHT, 0, stream>>>(x, base_hr, n * c, h, w_);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+int head_wgrad(const float* x, const void* dy, float* dw, float* db, int n, int h, int w_, int cout, int dtype,
+               float scale, cudaStream_t stream) {
+  if (n == 0 || h == 0 || w_ == 0) return LV_OK;
+  LV_CHECK_ARG(cout <= 64, "head wgrad: cout <= 64 (got %d)", cout);
+  LV_CHECK_ARG(n <= 65535, "head wgrad: batch too large for one launch");
+  dim3 grid((w_ + kGW - 1) / kGW, (h + kGH - 1) / kGH, n);
+  const size_t smem = static_cast<size_t>(kGH * kGW) * (cout + 1) * sizeof(float);
+  if (dtype == LV_F32)
+    head_wgrad_kernel<float><<<grid, 256, smem, stream>>>(x, static_cast<const float*>(dy), dw, db, n, h, w_, cout, scale);
+  else
+    head_wgrad_kernel<__nv_bfloat16><<<grid, 256, smem, stream>>>(x, static_cast<const __nv_bfloat16*>(dy), dw, db, n, h,
+                                                                  w_, cout, scale);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+}  // namespace lv

@@ -1,0 +1,221 @@
+// Operand packing and layout conversion helpers (HBM-bound, tiny).
+//   * weight packing: fp32 OIHW master weights -> the operand layout each conv kernel consumes
+//       LV_BF16: [ntile][src][tap][cin/8][cout_in_tile][8] bf16  (K-major SWIZZLE_NONE UMMA B operand, see conv_tc.cu)
+//       LV_F32 : [src][tap][cin][cout_pad] fp32                  (conv_simt.cu)
+//     with an optional "transpose" that yields the backward-data operand (180-degree rotated taps, in/out swapped).
+//   * NCHW fp32 <-> NHWC {bf16,fp32} at the Python module boundary (the reference's tensors are NCHW fp32,
+//     models/LarvaNet.py:163-171).
+//   * stand-alone L1 loss + sign gradient, fused AdamW.
+#include "lv_common.cuh"
+
+namespace lv {
+
+int pick_ntile(int cout_pad);
+
+constexpr int kMaxPackItems = 64;
+struct PackItemDev {
+  const float* w;
+  void* packed;
+  int O, I, transpose, i_off, i_cnt, cin, dtype;
+  int p_cout, p_cin_total, cout_pad, nt, nsrc;
+  long long total;  // packed elements
+};
+struct PackBatch {
+  PackItemDev it[kMaxPackItems];
+};
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackBatch batch) {
+  const PackItemDev& p = batch.it[blockIdx.y];
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < p.total; idx += static_cast<long long>(gridDim.x) * 256) {
+    int co, t, tap;
+    if (p.dtype == LV_BF16) {
+      long long r = idx;
+      const int e = static_cast<int>(r % 8); r /= 8;
+      const int co_in = static_cast<int>(r % p.nt); r /= p.nt;
+      const int ch = p.cin / 8;
+      const int chunk = static_cast<int>(r % ch); r /= ch;
+      tap = static_cast<int>(r % 9); r /= 9;
+      const int s = static_cast<int>(r % p.nsrc); r /= p.nsrc;
+      const int ntile = static_cast<int>(r);
+      co = ntile * p.nt + co_in;
+      t = s * p.cin + chunk * 8 + e;
+    } else {
+      long long r = idx;
+      co = static_cast<int>(r % p.cout_pad); r /= p.cout_pad;
+      const int ci = static_cast<int>(r % p.cin); r /= p.cin;
+      tap = static_cast<int>(r % 9); r /= 9;
+      const int s = static_cast<int>(r);
+      t = s * p.cin + ci;
+    }
+    float v = 0.f;
+    if (co < p.p_cout) {
+      int o, i, ky = tap / 3, kx = tap % 3;
+      if (p.transpose) {
+        o = t; i = p.i_off + co; ky = 2 - ky; kx = 2 - kx;
+      } else {
+        o = co; i = p.i_off + t;
+      }
+      v = p.w[((static_cast<size_t>(o) * p.I + i) * 3 + ky) * 3 + kx];
+    }
+    if (p.dtype == LV_BF16)
+      reinterpret_cast<__nv_bfloat16*>(p.packed)[idx] = __float2bfloat16_rn(v);
+    else
+      reinterpret_cast<float*>(p.packed)[idx] = v;
+  }
+}
+
+int pack_weights(const lv_pack_item* items, int count, cudaStream_t stream) {
+  if (count == 0) return LV_OK;
+  LV_CHECK_ARG(count > 0 && count <= kMaxPackItems, "pack: count must be in 1..%d", kMaxPackItems);
+  PackBatch batch;
+  long long max_total = 0;
+  for (int k = 0; k < count; ++k) {
+    const lv_pack_item& s = items[k];
+    PackItemDev& d = batch.it[k];
+    LV_CHECK_ARG(s.w != nullptr && s.packed != nullptr, "pack: null pointer in item %d", k);
+    LV_CHECK_ARG(s.cin > 0 && s.i_cnt > 0 && s.i_off >= 0 && s.i_off + s.i_cnt <= s.I, "pack: bad slice in item %d", k);
+    d.w = s.w; d.packed = s.packed; d.O = s.O; d.I = s.I; d.transpose = s.transpose; d.i_off = s.i_off;
+    d.i_cnt = s.i_cnt; d.cin = s.cin; d.dtype = s.dtype;
+    d.p_cout = s.transpose ? s.i_cnt : s.O;
+    d.p_cin_total = s.transpose ? s.O : s.i_cnt;
+    LV_CHECK_ARG(d.p_cin_total % s.cin == 0, "pack: cin_total %d not a multiple of per-source cin %d", d.p_cin_total, s.cin);
+    if (s.dtype == LV_BF16) LV_CHECK_ARG(s.cin % 16 == 0, "pack: bf16 operands need cin %% 16 == 0 (got %d)", s.cin);
+    d.nsrc = d.p_cin_total / s.cin;
+    d.cout_pad = (d.p_cout + 15) / 16 * 16;
+    d.nt = pick_ntile(d.cout_pad);
+    d.total = static_cast<long long>(d.cout_pad) * d.p_cin_total * 9;
+    if (d.total > max_total) max_total = d.total;
+  }
+  long long bx = (max_total + 255) / 256;
+  if (bx > 1024) bx = 1024;
+  pack_weights_kernel<<<dim3(static_cast<unsigned>(bx), count), 256, 0, stream>>>(batch);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long long HW, long long total) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int c = static_cast<int>(i % C);
+    const long long p = i / C;          // n*HW + hw
+    const long long n = p / HW, hw = p % HW;
+    dst[i] = from_f32<T>(src[(n * C + c) * HW + hw]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, long long HW, long long total) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const long long hw = i % HW;
+    const long long nc = i / HW;
+    const int c = static_cast<int>(nc % C);
+    const long long n = nc / C;
+    dst[i] = to_f32(src[(n * HW + hw) * C + c]);
+  }
+}
+
+static unsigned grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return static_cast<unsigned>(b < 1 ? 1 : b);
+}
+
+int nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dtype, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * c * h * w;
+  if (total == 0) return LV_OK;
+  if (dtype == LV_F32)
+    nchw_to_nhwc_kernel<float><<<grid_for(total), 256, 0, stream>>>(src, static_cast<float*>(dst), c, 1ll * h * w, total);
+  else
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), c,
+                                                                            1ll * h * w, total);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+int nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int dtype, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * c * h * w;
+  if (total == 0) return LV_OK;
+  if (dtype == LV_F32)
+    nhwc_to_nchw_kernel<float><<<grid_for(total), 256, 0, stream>>>(static_cast<const float*>(src), dst, c, 1ll * h * w, total);
+  else
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), dst, c,
+                                                                            1ll * h * w, total);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// L1 loss on HR fp32 NCHW images; thread = (n, c, y, x) LR position covering its 4x4 HR block.
+template <typename T>
+__global__ void __launch_bounds__(256)
+l1_loss_grad_kernel(const float* __restrict__ out, const float* __restrict__ truth, double* __restrict__ loss_sum,
+                    T* __restrict__ grad_sign, int N, int C, int H, int W) {
+  const long long total = static_cast<long long>(N) * C * H * W;
+  float loss = 0.f;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int c = static_cast<int>((i / (static_cast<long long>(W) * H)) % C);
+    const long long n = i / (static_cast<long long>(W) * H * C);
+    float g[16];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const size_t off = ((n * C + c) * (4ll * H) + (4 * y + r)) * (4ll * W) + 4 * x;
+      const float4 o = *reinterpret_cast<const float4*>(out + off);
+      const float4 t = *reinterpret_cast<const float4*>(truth + off);
+      const float d[4] = {o.x - t.x, o.y - t.y, o.z - t.z, o.w - t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        loss += fabsf(d[j]);
+        g[4 * r + j] = (d[j] > 0.f) ? 1.f : ((d[j] < 0.f) ? -1.f : 0.f);
+      }
+    }
+    if (grad_sign != nullptr) store16(grad_sign + ((n * H + y) * W + x) * (16ll * C) + 16 * c, g);
+  }
+  loss = warp_sum(loss);
+  if ((threadIdx.x & 31) == 0 && loss_sum != nullptr) atomicAdd(loss_sum, static_cast<double>(loss));
+}
+
+int l1_loss_grad(const float* out_hr, const float* truth_hr, double* loss_sum, void* grad_sign, int n, int c, int h, int w,
+                 int dtype, cudaStream_t stream) {
+  const long long total = static_cast<long long>(n) * c * h * w;
+  if (total == 0) return LV_OK;
+  if (dtype == LV_F32)
+    l1_loss_grad_kernel<float><<<grid_for(total), 256, 0, stream>>>(out_hr, truth_hr, loss_sum, static_cast<float*>(grad_sign),
+                                                                   n, c, h, w);
+  else
+    l1_loss_grad_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(
+        out_hr, truth_hr, loss_sum, static_cast<__nv_bfloat16*>(grad_sign), n, c, h, w);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AdamW over a flat arena, torch.optim.AdamW semantics (decoupled weight decay, bias-corrected).
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             long long numel, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < numel; i += static_cast<long long>(gridDim.x) * 256) {
+    const float grad = g[i] * gscale;
+    float pv = p[i] * (1.f - lr * wd);
+    const float mv = m[i] + (grad - m[i]) * (1.f - b1);            // lerp_, as torch does
+    const float vv = v[i] * b2 + (1.f - b2) * grad * grad;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv -= (lr / bc1) * (mv / denom);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+  }
+}
+
+int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, float grad_scale, cudaStream_t stream) {
+  if (numel == 0) return LV_OK;
+  LV_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  adamw_kernel<<<grid_for(numel), 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps,
+                                                    weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)),
+                                                    grad_scale);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+}  // namespace lv

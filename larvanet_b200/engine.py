@@ -1,0 +1,480 @@
+"""Fused execution engine for LarvaNet / LarvaNetV2: the whole forward (and backward) as a fixed chain of
+`lv_*` kernel launches over pre-allocated NHWC buffers, optionally replayed as one CUDA graph.
+
+What the reference does with ~40 Conv2d modules + autograd (models/LarvaNet.py:98-114, :287-293;
+models/LarvaNetV2.py:101-123, :355-365) becomes:
+
+  forward   head+bicubic kernel -> one conv kernel per Conv2d with bias/ReLU/residual/body-skip fused in the epilogue
+            -> exit conv writes PixelShuffle(4)+base (and, when training, the L1 partial sums and the sign gradient)
+  backward  one conv kernel per Conv2d for backward-data (180-degree rotated weights; ReLU mask and branch-gradient
+            accumulation fused in the epilogue), then BATCHED weight-gradient launches (one per body) that write
+            straight into a flat fp32 gradient arena, so zero_grad is one memset, the data-parallel exchange is one
+            allreduce per body slice and AdamW is one kernel.
+
+Activations are NHWC in `act_dtype` (bf16 = product path on tcgen05 tensor cores, fp32 = validation mode).
+Everything here is plumbing: tensors, streams, graphs.  No arithmetic happens in PyTorch.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+from ._lib import LV_EPI_NHWC, LV_EPI_PS4_NCHW, LarvaNetB200Error
+
+C = 48  # LarvaNet feature width (reference models/LarvaNet.py:226 -- hard-wired)
+
+
+class ParamArena:
+    """Flat fp32 parameter + gradient storage; every module parameter becomes a view into it (same shapes, same
+    state_dict keys), so the engine can hand raw offsets to the kernels and treat all gradients as one buffer."""
+
+    def __init__(self, module, device):
+        named = [(n, p) for n, p in module.named_parameters()]
+        self.names = [n for n, _ in named]
+        total = sum(p.numel() for _, p in named)
+        self.flat = torch.empty(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=device)
+        self.offsets = {}
+        self.views = {}
+        self.grad_views = {}
+        self.params = {}
+        off = 0
+        for n, p in named:
+            k = p.numel()
+            v = self.flat[off:off + k].view(p.shape)
+            v.copy_(p.data.to(device=device, dtype=torch.float32))
+            p.data = v
+            gv = self.grad[off:off + k].view(p.shape)
+            self.offsets[n] = (off, k)
+            self.views[n] = v
+            self.grad_views[n] = gv
+            self.params[n] = p
+            off += k
+        self.total = total
+
+    def attach_grads(self):
+        for n, p in self.params.items():
+            if p.requires_grad and p.grad is not self.grad_views[n]:
+                p.grad = self.grad_views[n]
+
+    def version(self):
+        return sum(p._version for p in self.params.values())
+
+    def slice_of(self, prefix):
+        """(start, end) element range covering all parameters whose name starts with `prefix`."""
+        lo, hi = None, None
+        for n in self.names:
+            if n.startswith(prefix):
+                o, k = self.offsets[n]
+                lo = o if lo is None else min(lo, o)
+                hi = o + k if hi is None else max(hi, o + k)
+        return lo, hi
+
+
+class _Bufs:
+    pass
+
+
+class LarvaEngine:
+    def __init__(self, module, blocks, v2=False, act_dtype=torch.bfloat16, device=None, use_graphs=None):
+        self.module = module
+        self.blocks = list(blocks)
+        self.m = len(self.blocks)
+        self.v2 = bool(v2)
+        self.act_dtype = act_dtype
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != 'cuda':
+            raise LarvaNetB200Error('larvanet_b200 runs on CUDA devices only (no CPU fallback)')
+        self.sm_count = ops.device_check(self.device.index)
+        if use_graphs is None:
+            use_graphs = os.environ.get('LARVANET_B200_GRAPHS', '1') != '0'
+        self.use_graphs = use_graphs
+        self.max_ctas = int(os.environ.get('LARVANET_B200_MAX_CTAS', '0'))
+        self.wgrad_splits = int(os.environ.get('LARVANET_B200_WGRAD_SPLITS', '0'))
+        self.arena = ParamArena(module, self.device)
+        self._conv_layers = self._enumerate_convs()
+        self._alloc_packed()
+        self._packed_version = None
+        self._packed_bwd = False
+        self._infer = {}   # shape -> (bufs, graph)
+        self._train = {}
+        self.simt = False  # tests flip this to cross-check the tensor-core kernels on CUDA cores
+        # data parallel
+        self.world_size = 1
+        self.process_group = None
+
+    # ------------------------------------------------------------------ layers / packed weights
+    def _enumerate_convs(self):
+        layers = []  # (prefix, O, I)
+        for i, nb in enumerate(self.blocks):
+            for j in range(nb):
+                for k in (0, 2):
+                    layers.append((f'body_{i}.res_blocks.{j}.body.{k}', C, C))
+            for k in (0, 2):
+                layers.append((f'body_{i}.leg.recon_block.{k}', C, C))
+        if self.v2:
+            layers.append(('tail.merge_conv', C, C * self.m))
+            for k in (0, 2):
+                layers.append((f'tail.recon_block.{k}', C, C))
+        return layers
+
+    def _alloc_packed(self):
+        dt = self.act_dtype
+        self._pk = {}      # (prefix, 'fwd') / (prefix, 'bwd', s) -> uint8 view
+        items_f, items_b = [], []
+        sizes = []
+        for prefix, O, I in self._conv_layers:
+            sizes.append(((prefix, 'fwd'), ops.packed_weight_bytes(O, I, dt)))
+            for s in range(I // C):
+                sizes.append(((prefix, 'bwd', s), ops.packed_weight_bytes(C, O, dt)))
+        total = sum((b + 255) // 256 * 256 for _, b in sizes)
+        self._packed = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        off = 0
+        for key, b in sizes:
+            self._pk[key] = self._packed[off:off + b]
+            off += (b + 255) // 256 * 256
+        for prefix, O, I in self._conv_layers:
+            w = self.arena.views[prefix + '.weight']
+            items_f.append(dict(w=w, packed=self._pk[(prefix, 'fwd')], transpose=0, i_off=0, i_cnt=I, cin=C, dtype=dt))
+            for s in range(I // C):
+                items_b.append(dict(w=w, packed=self._pk[(prefix, 'bwd', s)], transpose=1, i_off=C * s, i_cnt=C, cin=C,
+                                    dtype=dt))
+        self._pack_items_fwd, self._pack_items_bwd = items_f, items_b
+
+    def repack(self, backward=False, force=False):
+        """Refresh the packed bf16/fp32 conv operands from the fp32 master weights when they changed."""
+        ver = self.arena.version()
+        if not force and ver == self._packed_version and (self._packed_bwd or not backward):
+            return
+        items = self._pack_items_fwd + (self._pack_items_bwd if backward else [])
+        ops.pack_weights(items)
+        self._packed_version = ver
+        self._packed_bwd = backward
+
+    def mark_weights_changed(self):
+        self._packed_version = None
+
+    # ------------------------------------------------------------------ helpers
+    def _w(self, prefix):
+        return self.arena.views[prefix + '.weight'], self.arena.views[prefix + '.bias']
+
+    def _conv(self, srcs, prefix, out=None, **kw):
+        _, b = self._w(prefix)
+        ops.conv3x3(srcs, self._pk[(prefix, 'fwd')], C, bias=b, out=out, max_ctas=self.max_ctas, simt=self.simt, **kw)
+
+    def _dgrad(self, dy, prefix, out, s=0, **kw):
+        ops.conv3x3([dy], self._pk[(prefix, 'bwd', s)], C, bias=None, out=out, max_ctas=self.max_ctas, simt=self.simt,
+                    **kw)
+
+    def _act(self, n, h, w, c=C):
+        return torch.empty((n, h, w, c), dtype=self.act_dtype, device=self.device)
+
+    # ------------------------------------------------------------------ inference
+    def _build_infer(self, n, h, w, exit_leg=None):
+        b = _Bufs()
+        b.x = torch.empty((n, 3, h, w), dtype=torch.float32, device=self.device)
+        b.base = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=self.device)
+        b.out = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=self.device)
+        b.f0 = self._act(n, h, w)
+        b.t = self._act(n, h, w)
+        b.pp = [self._act(n, h, w), self._act(n, h, w)]
+        b.feats = [self._act(n, h, w) for _ in range(self.m)]
+        b.u = self._act(n, h, w)
+        b.mf = self._act(n, h, w) if self.v2 else None
+        return b
+
+    def _run_infer(self, b, exit_leg=None):
+        hw, hb = self._w('head.feature_extraction')
+        k = self.m if exit_leg is None else exit_leg
+        ops.head_bicubic(b.x, hw, hb, b.f0, b.base)
+        if k == 0:
+            b.out.copy_(b.base)
+            return
+        fin = b.f0
+        for i in range(k):
+            a = fin
+            nb = self.blocks[i]
+            for j in range(nb):
+                p = f'body_{i}.res_blocks.{j}.body'
+                self._conv([a], p + '.0', out=b.t, relu=True)
+                last = j == nb - 1
+                dst = b.feats[i] if last else b.pp[j & 1]
+                self._conv([b.t], p + '.2', out=dst, res1=a, res2=fin if last else None)
+                a = dst
+            if nb == 0:  # empty body: x + x
+                raise LarvaNetB200Error('num_blocks entries must be >= 1')
+            fin = b.feats[i]
+        if self.v2 and exit_leg is None:
+            self._conv(b.feats, 'tail.merge_conv', out=b.mf)
+            self._conv([b.mf], 'tail.recon_block.0', out=b.u, relu=True)
+            self._conv([b.u], 'tail.recon_block.2', epilogue=LV_EPI_PS4_NCHW, out_hr=b.out, base_hr=b.base)
+        else:
+            p = f'body_{k - 1}.leg.recon_block'
+            self._conv([fin], p + '.0', out=b.u, relu=True)
+            self._conv([b.u], p + '.2', epilogue=LV_EPI_PS4_NCHW, out_hr=b.out, base_hr=b.base)
+
+    def forward(self, x, exit_leg=None):
+        """x: fp32 NCHW [n,3,h,w] CUDA tensor on the 0..255 scale -> fp32 NCHW [n,3,4h,4w] (engine-owned buffer)."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise LarvaNetB200Error(f'expected NCHW input with 3 channels, got {tuple(x.shape)}')
+        n, _, h, w = (int(v) for v in x.shape)
+        self.repack(backward=False)
+        key = (n, h, w, exit_leg)
+        ent = self._infer.get(key)
+        if ent is None:
+            ent = [self._build_infer(n, h, w), None]
+            self._infer[key] = ent
+        b = ent[0]
+        b.x.copy_(x.to(dtype=torch.float32), non_blocking=True)
+        if n * h * w == 0:
+            return b.out
+        if self.use_graphs and not self.simt:
+            if ent[1] is None:
+                self._run_infer(b, exit_leg)  # warm-up (also sets func attributes outside capture)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_infer(b, exit_leg)
+                ent[1] = g
+            ent[1].replay()
+        else:
+            self._run_infer(b, exit_leg)
+        return b.out
+
+    # ------------------------------------------------------------------ training
+    def _build_train(self, n, h, w):
+        b = _Bufs()
+        dev = self.device
+        b.x = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+        b.truth = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=dev)
+        b.base = torch.empty_like(b.truth)
+        b.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        b.f0 = self._act(n, h, w)
+        b.t = [[self._act(n, h, w) for _ in range(nb)] for nb in self.blocks]       # post-ReLU of conv1
+        b.a = [[self._act(n, h, w) for _ in range(nb - 1)] for nb in self.blocks]   # block outputs (not the last)
+        b.feats = [self._act(n, h, w) for _ in range(self.m)]                       # body outputs
+        b.u = [self._act(n, h, w) for _ in range(self.m)]                           # leg post-ReLU
+        b.g = [self._act(n, h, w) for _ in range(self.m)]                           # leg sign gradient (dY of recon.2)
+        b.du = [self._act(n, h, w) for _ in range(self.m)]                          # dY of leg recon.0
+        b.dt = [[self._act(n, h, w) for _ in range(nb)] for nb in self.blocks]      # dY of block conv1
+        b.da = [[self._act(n, h, w) for _ in range(nb)] for nb in self.blocks]      # dY of block conv2 (= d block out)
+        b.dfin = [self._act(n, h, w) for _ in range(self.m)]                        # gradient wrt each body's input
+        if self.v2:
+            b.mf, b.ut, b.gt, b.dut, b.dmf = (self._act(n, h, w) for _ in range(5))
+            b.dfeat = [self._act(n, h, w) for _ in range(self.m)]
+        b.exits = None
+        # weight-gradient batches, one per body (+ tail), in arena order
+        numel = n * 3 * 16 * h * w
+        denom = self.m + 1 if self.v2 else self.m
+        b.scale = 1.0 / (float(numel) * denom)
+        gv = self.arena.grad_views
+        b.wgrad = []
+        splits = self.wgrad_splits
+        tiles = n * ((h + 15) // 16) * ((w + 7) // 8)
+        for i, nb in enumerate(self.blocks):
+            items = []
+            fin = b.f0 if i == 0 else b.feats[i - 1]
+            for j in range(nb):
+                p = f'body_{i}.res_blocks.{j}.body'
+                a_in = fin if j == 0 else b.a[i][j - 1]
+                items.append(dict(x=a_in, dy=b.dt[i][j], dw=gv[p + '.0.weight'], db=gv[p + '.0.bias']))
+                items.append(dict(x=b.t[i][j], dy=b.da[i][j], dw=gv[p + '.2.weight'], db=gv[p + '.2.bias']))
+            p = f'body_{i}.leg.recon_block'
+            items.append(dict(x=b.feats[i], dy=b.du[i], dw=gv[p + '.0.weight'], db=gv[p + '.0.bias']))
+            items.append(dict(x=b.u[i], dy=b.g[i], dw=gv[p + '.2.weight'], db=gv[p + '.2.bias']))
+            b.wgrad.append(self._make_wgrad(items, tiles, splits))
+        if self.v2:
+            items = []
+            for s in range(self.m):
+                items.append(dict(x=b.feats[s], dy=b.dmf, dw=gv['tail.merge_conv.weight'],
+                                  db=gv['tail.merge_conv.bias'] if s == 0 else None, cin_total=C * self.m, cin_off=C * s))
+            items.append(dict(x=b.mf, dy=b.dut, dw=gv['tail.recon_block.0.weight'], db=gv['tail.recon_block.0.bias']))
+            items.append(dict(x=b.ut, dy=b.gt, dw=gv['tail.recon_block.2.weight'], db=gv['tail.recon_block.2.bias']))
+            b.wgrad_tail = self._make_wgrad(items, tiles, splits)
+        return b
+
+    def _make_wgrad(self, items, tiles, splits):
+        if splits <= 0:
+            # ~2 CTAs worth of layers per SM in total, at least 1 and at most one split per tile
+            splits = max(1, min(tiles, (2 * self.sm_count + len(items) - 1) // len(items)))
+        return ops.WgradBatch(items, splits, self.device)
+
+    def set_data_parallel(self, world_size, process_group=None):
+        self.world_size = int(world_size)
+        self.process_group = process_group
+        self._train.clear()
+
+    def _run_train(self, b):
+        """forward with saved activations + fused losses, then backward-data chain and batched weight gradients."""
+        hw, hb = self._w('head.feature_extraction')
+        scale = b.scale / self.world_size
+        b.loss_sum.zero_()
+        self.arena.grad.zero_()
+        ops.head_bicubic(b.x, hw, hb, b.f0, b.base)
+        # ---------------- forward ----------------
+        fin = b.f0
+        for i, nb in enumerate(self.blocks):
+            a = fin
+            for j in range(nb):
+                p = f'body_{i}.res_blocks.{j}.body'
+                self._conv([a], p + '.0', out=b.t[i][j], relu=True)
+                last = j == nb - 1
+                dst = b.feats[i] if last else b.a[i][j]
+                self._conv([b.t[i][j]], p + '.2', out=dst, res1=a, res2=fin if last else None)
+                a = dst
+            fin = b.feats[i]
+            p = f'body_{i}.leg.recon_block'
+            self._conv([fin], p + '.0', out=b.u[i], relu=True)
+            self._conv([b.u[i]], p + '.2', epilogue=LV_EPI_PS4_NCHW, base_hr=b.base, truth_hr=b.truth,
+                       loss_sum=b.loss_sum, grad_sign=b.g[i],
+                       out_hr=b.exits[i] if b.exits is not None else None)
+        if self.v2:
+            self._conv(b.feats, 'tail.merge_conv', out=b.mf)
+            self._conv([b.mf], 'tail.recon_block.0', out=b.ut, relu=True)
+            self._conv([b.ut], 'tail.recon_block.2', epilogue=LV_EPI_PS4_NCHW, base_hr=b.base, truth_hr=b.truth,
+                       loss_sum=b.loss_sum, grad_sign=b.gt,
+                       out_hr=b.exits[self.m] if b.exits is not None else None)
+        # ---------------- backward ----------------
+        if self.v2:
+            self._dgrad(b.gt, 'tail.recon_block.2', out=b.dut, mask=b.ut)
+            self._dgrad(b.dut, 'tail.recon_block.0', out=b.dmf)
+            for s in range(self.m):
+                self._dgrad(b.dmf, 'tail.merge_conv', out=b.dfeat[s], s=s)
+            b.wgrad_tail.launch(simt=self.simt)
+        dnext = None
+        for i in reversed(range(self.m)):
+            nb = self.blocks[i]
+            p = f'body_{i}.leg.recon_block'
+            self._dgrad(b.g[i], p + '.2', out=b.du[i], mask=b.u[i])
+            # gradient wrt the body output = leg branch + next body's input gradient (+ tail branch)
+            dfout = b.da[i][nb - 1]
+            self._dgrad(b.du[i], p + '.0', out=dfout, res1=dnext, res2=b.dfeat[i] if self.v2 else None)
+            for j in reversed(range(nb)):
+                pj = f'body_{i}.res_blocks.{j}.body'
+                self._dgrad(b.da[i][j], pj + '.2', out=b.dt[i][j], mask=b.t[i][j])
+                dst = b.dfin[i] if j == 0 else b.da[i][j - 1]
+                self._dgrad(b.dt[i][j], pj + '.0', out=dst, res1=b.da[i][j], res2=dfout if j == 0 else None)
+            dnext = b.dfin[i]
+            b.wgrad[i].launch(simt=self.simt)
+        ops.head_wgrad(b.x, b.dfin[0], self.arena.grad_views['head.feature_extraction.weight'],
+                       self.arena.grad_views['head.feature_extraction.bias'], scale)
+
+    def train_step(self, x, truth, keep_exits=False):
+        """One forward+backward.  Leaves d(loss)/d(param) in the gradient arena (== every param.grad) and returns the
+        multi-exit loss as a 0-dim float64 CUDA tensor (no host sync).  Restates models/LarvaNet.py:102-113 /
+        models/LarvaNetV2.py:105-120 (everything before optim.step())."""
+        n, _, h, w = (int(v) for v in x.shape)
+        if tuple(truth.shape) != (n, 3, 4 * h, 4 * w):
+            raise LarvaNetB200Error(f'truth shape {tuple(truth.shape)} does not match 4x input {tuple(x.shape)}')
+        self.repack(backward=True)
+        key = (n, h, w, bool(keep_exits))
+        ent = self._train.get(key)
+        if ent is None:
+            b = self._build_train(n, h, w)
+            if keep_exits:
+                b.exits = [torch.empty_like(b.truth) for _ in range(self.m + (1 if self.v2 else 0))]
+            scale = b.scale / self.world_size
+            for wb in b.wgrad + ([b.wgrad_tail] if self.v2 else []):
+                wb.set_scale(scale)
+            ent = [b, None]
+            self._train[key] = ent
+        b = ent[0]
+        b.x.copy_(x, non_blocking=True)
+        b.truth.copy_(truth, non_blocking=True)
+        self.arena.attach_grads()
+        if self.use_graphs and not self.simt:
+            if ent[1] is None:
+                self._run_train(b)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_train(b)
+                ent[1] = g
+            ent[1].replay()
+        else:
+            self._run_train(b)
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.arena.grad, group=self.process_group)
+            dist.all_reduce(b.loss_sum, group=self.process_group)
+        denom = self.m + 1 if self.v2 else self.m
+        numel = n * 3 * 16 * h * w * self.world_size
+        self.last_exits = b.exits
+        return b.loss_sum[0] / (float(numel) * denom)
+
+    # ------------------------------------------------------------------ individually-callable modules
+    # The reference's train step and analysis scripts call sub-modules one by one with NCHW fp32 tensors
+    # (models/LarvaNet.py:102-107, validate_tree.py:94-96).  These helpers keep that surface: convert at the
+    # boundary, run the same kernels eagerly.  Forward only (no autograd graph is recorded).
+    def _to_act(self, x_nchw):
+        x = x_nchw.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        n, c, h, w = (int(v) for v in x.shape)
+        a = torch.empty((n, h, w, c), dtype=self.act_dtype, device=self.device)
+        ops.nchw_to_nhwc(x, a)
+        return a
+
+    def _to_nchw(self, a):
+        n, h, w, c = (int(v) for v in a.shape)
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=self.device)
+        ops.nhwc_to_nchw(a, y)
+        return y
+
+    def run_head(self, x):
+        self.repack()
+        x = x.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        n, _, h, w = (int(v) for v in x.shape)
+        hw, hb = self._w('head.feature_extraction')
+        fea = self._act(n, h, w)
+        ops.head_bicubic(x, hw, hb, fea, None)
+        return self._to_nchw(fea)
+
+    def run_base(self, x):
+        x = x.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        n, c, h, w = (int(v) for v in x.shape)
+        out = torch.empty((n, c, 4 * h, 4 * w), dtype=torch.float32, device=self.device)
+        ops.bicubic_x4(x, out)
+        return out
+
+    def _resblock(self, i, j, a, fin=None):
+        n, h, w, _ = (int(v) for v in a.shape)
+        p = f'body_{i}.res_blocks.{j}.body'
+        t, o = self._act(n, h, w), self._act(n, h, w)
+        self._conv([a], p + '.0', out=t, relu=True)
+        self._conv([t], p + '.2', out=o, res1=a, res2=fin)
+        return o
+
+    def run_resblock(self, i, j, x):
+        self.repack()
+        return self._to_nchw(self._resblock(i, j, self._to_act(x)))
+
+    def run_body(self, i, x):
+        self.repack()
+        fin = self._to_act(x)
+        a = fin
+        nb = self.blocks[i]
+        for j in range(nb):
+            a = self._resblock(i, j, a, fin if j == nb - 1 else None)
+        return self._to_nchw(a)
+
+    def _recon(self, prefix, fea, base):
+        n, h, w, _ = (int(v) for v in fea.shape)
+        base = base.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        u = self._act(n, h, w)
+        out = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=self.device)
+        self._conv([fea], prefix + '.recon_block.0', out=u, relu=True)
+        self._conv([u], prefix + '.recon_block.2', epilogue=LV_EPI_PS4_NCHW, out_hr=out, base_hr=base)
+        return out
+
+    def run_leg(self, i, fea, base):
+        self.repack()
+        return self._recon(f'body_{i}.leg', self._to_act(fea), base)
+
+    def run_tail(self, features, base):
+        self.repack()
+        feats = [self._to_act(f) for f in features]
+        n, h, w, _ = (int(v) for v in feats[0].shape)
+        mf = self._act(n, h, w)
+        self._conv(feats, 'tail.merge_conv', out=mf)
+        return self._recon('tail', mf, base)

@@ -1,0 +1,211 @@
+"""Tensor-level wrappers over the C-ABI: validate torch tensors, pass raw device pointers + the current stream.
+
+PyTorch is only the owner of device memory and streams here; every function ends in exactly one `lv_*` call.
+No function in this file has a fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (LV_BF16, LV_EPI_NHWC, LV_EPI_PS2_NHWC, LV_EPI_PS4_NCHW, LV_EPI_RGB_NCHW, LV_F32, ConvArgs,
+                   PackItem, WgradItem, check)
+
+_TORCH2LV = {torch.float32: LV_F32, torch.bfloat16: LV_BF16}
+
+
+def dtype_id(dt):
+    try:
+        return _TORCH2LV[dt]
+    except KeyError:
+        raise _lib.LarvaNetB200Error(f'unsupported activation dtype {dt}; use torch.bfloat16 or torch.float32') from None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, name='tensor'):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.LarvaNetB200Error(f'{name} must be a CUDA tensor (no CPU fallback)')
+    if not t.is_contiguous():
+        raise _lib.LarvaNetB200Error(f'{name} must be contiguous')
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.LarvaNetB200Error(f'{name} must be {dtype}, got {t.dtype}')
+    return t.data_ptr()
+
+
+def device_check(device_index=None):
+    lib = _lib.load()
+    dev = torch.cuda.current_device() if device_index is None else device_index
+    sm = C.c_int(0)
+    check(lib.lv_device_check(dev, C.byref(sm)), 'lv_device_check')
+    return sm.value
+
+
+def packed_weight_bytes(cout, cin_total, dt):
+    return int(_lib.load().lv_packed_weight_bytes(cout, cin_total, dtype_id(dt)))
+
+
+def pack_weights(items):
+    """items: list of dicts(w=fp32 OIHW tensor, packed=uint8/any tensor, transpose, i_off, i_cnt, cin, dtype)."""
+    lib = _lib.load()
+    for start in range(0, len(items), 64):
+        chunk = items[start:start + 64]
+        arr = (PackItem * len(chunk))()
+        for k, it in enumerate(chunk):
+            w = it['w']
+            O, I = int(w.shape[0]), int(w.shape[1])
+            assert w.shape[2] == 3 and w.shape[3] == 3
+            arr[k].w = _ptr(w, torch.float32, 'weight')
+            arr[k].packed = _ptr(it['packed'], None, 'packed')
+            arr[k].O, arr[k].I = O, I
+            arr[k].transpose = int(it.get('transpose', 0))
+            arr[k].i_off = int(it.get('i_off', 0))
+            arr[k].i_cnt = int(it.get('i_cnt', I))
+            arr[k].cin = int(it['cin'])
+            arr[k].dtype = dtype_id(it['dtype'])
+        check(lib.lv_pack_conv3x3_weights(arr, len(chunk), _stream()), 'lv_pack_conv3x3_weights')
+
+
+def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res1=None, res2=None, out=None,
+                   epilogue=LV_EPI_NHWC, out_hr=None, base_hr=None, truth_hr=None, loss_sum=None, grad_sign=None,
+                   post_w=None, post_b=None, res_scale=1.0):
+    """Build an lv_conv_args from torch tensors.  srcs: list of NHWC [n,h,w,cin] tensors (same shape/dtype)."""
+    x0 = srcs[0]
+    dt = x0.dtype
+    n, h, w, cin = (int(v) for v in x0.shape)
+    a = ConvArgs()
+    a.n, a.h, a.w, a.cin, a.num_src, a.cout = n, h, w, cin, len(srcs), int(cout)
+    a.dtype = dtype_id(dt)
+    a.relu = int(bool(relu))
+    a.epilogue = int(epilogue)
+    a.res_scale = float(res_scale)
+    for i, s in enumerate(srcs):
+        if tuple(s.shape) != tuple(x0.shape):
+            raise _lib.LarvaNetB200Error('all conv sources must have the same shape')
+        a.src[i] = _ptr(s, dt, f'src[{i}]')
+    a.weights = _ptr(weights, None, 'weights')
+    a.bias = _ptr(bias, torch.float32, 'bias')
+    a.mask = _ptr(mask, dt, 'mask')
+    a.res1 = _ptr(res1, dt, 'res1')
+    a.res2 = _ptr(res2, dt, 'res2')
+    a.out = _ptr(out, dt, 'out')
+    a.out_hr = _ptr(out_hr, torch.float32, 'out_hr')
+    a.base_hr = _ptr(base_hr, torch.float32, 'base_hr')
+    a.truth_hr = _ptr(truth_hr, torch.float32, 'truth_hr')
+    a.loss_sum = _ptr(loss_sum, torch.float64, 'loss_sum')
+    a.grad_sign = _ptr(grad_sign, dt, 'grad_sign')
+    a.post_w = _ptr(post_w, torch.float32, 'post_w')
+    a.post_b = _ptr(post_b, torch.float32, 'post_b')
+    return a
+
+
+def conv3x3_launch(args, max_ctas=0, simt=False):
+    lib = _lib.load()
+    if simt:
+        check(lib.lv_conv3x3_simt(C.byref(args), _stream()), 'lv_conv3x3_simt')
+    else:
+        check(lib.lv_conv3x3(C.byref(args), int(max_ctas), _stream()), 'lv_conv3x3')
+
+
+def conv3x3(srcs, weights, cout, max_ctas=0, simt=False, **kw):
+    conv3x3_launch(make_conv_args(srcs, weights, cout, **kw), max_ctas, simt)
+
+
+def head_bicubic(x, w, b, fea, base_hr=None, pre_w=None, pre_b=None):
+    """x fp32 NCHW [n,3,h,w] -> fea NHWC [n,h,w,cout] (+ base_hr fp32 NCHW [n,3,4h,4w])."""
+    n, c, h, wd = (int(v) for v in x.shape)
+    assert c == 3
+    cout = int(w.shape[0])
+    check(_lib.load().lv_head_bicubic_fwd(
+        _ptr(x, torch.float32, 'x'), _ptr(w, torch.float32, 'head weight'), _ptr(b, torch.float32, 'head bias'),
+        _ptr(pre_w, torch.float32, 'pre_w'), _ptr(pre_b, torch.float32, 'pre_b'), _ptr(fea, None, 'fea'),
+        _ptr(base_hr, torch.float32, 'base_hr'), n, h, wd, cout, dtype_id(fea.dtype), _stream()), 'lv_head_bicubic_fwd')
+
+
+def bicubic_x4(x, out):
+    n, c, h, w = (int(v) for v in x.shape)
+    check(_lib.load().lv_bicubic_x4(_ptr(x, torch.float32, 'x'), _ptr(out, torch.float32, 'out'), n, c, h, w, _stream()),
+          'lv_bicubic_x4')
+
+
+def head_wgrad(x, dy, dw, db, scale):
+    n, c, h, w = (int(v) for v in x.shape)
+    cout = int(dy.shape[3])
+    check(_lib.load().lv_head_wgrad(_ptr(x, torch.float32, 'x'), _ptr(dy, None, 'dy'), _ptr(dw, torch.float32, 'dw'),
+                                    _ptr(db, torch.float32, 'db'), n, h, w, cout, dtype_id(dy.dtype), float(scale),
+                                    _stream()), 'lv_head_wgrad')
+
+
+class WgradBatch:
+    """A prepared batch of weight-gradient items: host ctypes array + its device copy + split-K workspace."""
+
+    def __init__(self, items, splits, device):
+        lib = _lib.load()
+        self.count = len(items)
+        self.splits = int(splits)
+        self.host = (WgradItem * self.count)()
+        self._keep = []
+        for k, it in enumerate(items):
+            x, dy, dw, db = it['x'], it['dy'], it['dw'], it.get('db')
+            n, h, w, cin = (int(v) for v in x.shape)
+            hi = self.host[k]
+            hi.n, hi.h, hi.w, hi.cin, hi.cout = n, h, w, cin, int(dy.shape[3])
+            hi.cin_total = int(it.get('cin_total', cin))
+            hi.cin_off = int(it.get('cin_off', 0))
+            hi.dtype = dtype_id(x.dtype)
+            hi.x, hi.dy = _ptr(x, None, 'x'), _ptr(dy, x.dtype, 'dy')
+            hi.dw, hi.db = _ptr(dw, torch.float32, 'dw'), _ptr(db, torch.float32, 'db')
+            hi.scale = float(it.get('scale', 1.0))
+            self._keep.append((x, dy, dw, db))
+        raw = bytes(self.host)
+        self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        ws = int(lib.lv_wgrad_workspace_bytes(self.host, self.count, self.splits))
+        self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=device)
+
+    def set_scale(self, scale):
+        """Rewrite every item's scale (host + device copies)."""
+        for k in range(self.count):
+            self.host[k].scale = float(scale)
+        self.dev.copy_(torch.frombuffer(bytearray(bytes(self.host)), dtype=torch.uint8), non_blocking=False)
+
+    def launch(self, simt=False):
+        lib = _lib.load()
+        if simt:
+            check(lib.lv_conv3x3_wgrad_simt(self.host, self.dev.data_ptr(), self.count, self.splits, _stream()),
+                  'lv_conv3x3_wgrad_simt')
+        else:
+            check(lib.lv_conv3x3_wgrad(self.host, self.dev.data_ptr(), self.count, self.splits,
+                                       self.workspace.data_ptr(), _stream()), 'lv_conv3x3_wgrad')
+
+
+def nchw_to_nhwc(src, dst):
+    n, c, h, w = (int(v) for v in src.shape)
+    check(_lib.load().lv_nchw_to_nhwc(_ptr(src, torch.float32, 'src'), _ptr(dst, None, 'dst'), n, c, h, w,
+                                      dtype_id(dst.dtype), _stream()), 'lv_nchw_to_nhwc')
+
+
+def nhwc_to_nchw(src, dst):
+    n, h, w, c = (int(v) for v in src.shape)
+    check(_lib.load().lv_nhwc_to_nchw(_ptr(src, None, 'src'), _ptr(dst, torch.float32, 'dst'), n, c, h, w,
+                                      dtype_id(src.dtype), _stream()), 'lv_nhwc_to_nchw')
+
+
+def l1_loss_grad(out_hr, truth_hr, loss_sum, grad_sign=None):
+    n, c, h4, w4 = (int(v) for v in out_hr.shape)
+    dt = dtype_id(grad_sign.dtype) if grad_sign is not None else LV_F32
+    check(_lib.load().lv_l1_loss_grad(_ptr(out_hr, torch.float32, 'out'), _ptr(truth_hr, torch.float32, 'truth'),
+                                      _ptr(loss_sum, torch.float64, 'loss_sum'), _ptr(grad_sign, None, 'grad_sign'),
+                                      n, c, h4 // 4, w4 // 4, dt, _stream()), 'lv_l1_loss_grad')
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    check(_lib.load().lv_adamw_step(_ptr(param, torch.float32, 'param'), _ptr(grad, torch.float32, 'grad'),
+                                    _ptr(exp_avg, torch.float32, 'exp_avg'), _ptr(exp_avg_sq, torch.float32, 'exp_avg_sq'),
+                                    param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                    int(step), float(grad_scale), _stream()), 'lv_adamw_step')
