@@ -149,7 +149,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug must surface as a trapped kernel (CUDA error at the next sync), never as a hung GPU.
 #ifndef LV_SPIN_LIMIT
-#define LV_SPIN_LIMIT (1u << 26)
+#define LV_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;

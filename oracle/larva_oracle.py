@@ -251,12 +251,16 @@ def larvanet_v2_forward(params, x, blocks, dtype=np.float64):
     return out
 
 
-def larvanet_train_step(params, x, truth, blocks, v2=False, dtype=np.float64):
+def larvanet_train_step(params, x, truth, blocks, v2=False, dtype=np.float64, sign_from=None):
     """Forward + backward core of train_step_larva.
 
     V1: reference models/LarvaNet.py:102-113 -- loss = sum_i L1(leg_i(body_i(..)), truth) / M.
     V2: reference models/LarvaNetV2.py:105-118 -- M leg losses + tail loss, divided by M+1.
     Returns (loss, grads dict keyed like state_dict, list of per-exit outputs).
+
+    `sign_from` (optional list of per-exit output arrays) replaces the oracle's own exit outputs inside
+    sign(out - truth) only.  The L1 gradient is discontinuous, so a parity test of the BACKWARD kernels feeds the
+    device's exit outputs here; the pure-oracle gradient (sign_from=None) is what is pinned to the reference.
     """
     x = np.asarray(x, dtype)
     truth = np.asarray(truth, dtype)
@@ -287,16 +291,18 @@ def larvanet_train_step(params, x, truth, blocks, v2=False, dtype=np.float64):
     grads = {}
     dfeats = [np.zeros_like(f) for f in feats]
     if v2:
-        dmfea = _recon_bwd(params, 'tail', ttp, l1_loss_grad(tout, truth, 1.0 / denom), grads, dtype)
+        souts = outs if sign_from is None else [np.asarray(o, dtype) for o in sign_from]
+        dmfea = _recon_bwd(params, 'tail', ttp, l1_loss_grad(souts[m], truth, 1.0 / denom), grads, dtype)
         dcat, dmw, dmb = conv2d_backward(cat, mw, dmfea)
         grads['tail.merge_conv.weight'] = dmw
         grads['tail.merge_conv.bias'] = dmb
         for i in range(m):
             dfeats[i] = dfeats[i] + dcat[:, NUM_FILTERS * i:NUM_FILTERS * (i + 1)]
+    souts = outs if sign_from is None else [np.asarray(o, dtype) for o in sign_from]
     dnext = None
     for i in reversed(range(m)):
         d = dfeats[i] + _recon_bwd(params, f'body_{i}.leg', leg_tapes[i],
-                                   l1_loss_grad(outs[i], truth, 1.0 / denom), grads, dtype)
+                                   l1_loss_grad(souts[i], truth, 1.0 / denom), grads, dtype)
         if dnext is not None:
             d = d + dnext
         dnext = _body_bwd(params, i, body_tapes[i], d, grads, dtype)

@@ -1,0 +1,255 @@
+"""Kernel-level parity tests through the C-ABI (ctypes), `-m gpu` only.
+
+Every test feeds the CUDA kernel and the numpy oracle the SAME operands (for bf16: the oracle gets the bf16-rounded
+values as float64), so the only differences are fp32-vs-fp64 accumulation and the final store rounding:
+  bf16 store: |err| <= 2^-8 * |ref| + small abs;   fp32 mode: <= 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from larvanet_b200 import _lib, ops
+from oracle import larva_oracle as O
+from tests.gpu_util import bf16_round, from_nhwc, rel_l2, to_nhwc
+
+pytestmark = pytest.mark.gpu
+
+DT = {'bf16': torch.bfloat16, 'fp32': torch.float32}
+
+
+def _rand_conv(rs, cout, cin_total, dtype, wscale=0.05):
+    w = (rs.standard_normal((cout, cin_total, 3, 3)) * wscale).astype(np.float32)
+    b = (rs.standard_normal(cout) * 0.5).astype(np.float32)
+    wq = bf16_round(w) if dtype == torch.bfloat16 else w.astype(np.float64)
+    return w, b, wq
+
+
+def _pack(w, dtype, cin, transpose=0, i_off=0, i_cnt=None):
+    wt = torch.from_numpy(w).cuda()
+    O_, I_ = w.shape[:2]
+    i_cnt = I_ if i_cnt is None else i_cnt
+    p_cout, p_cin_total = (i_cnt, O_) if transpose else (O_, i_cnt)
+    packed = torch.zeros(ops.packed_weight_bytes(p_cout, p_cin_total, dtype), dtype=torch.uint8, device='cuda')
+    ops.pack_weights([dict(w=wt, packed=packed, transpose=transpose, i_off=i_off, i_cnt=i_cnt, cin=cin, dtype=dtype)])
+    return packed
+
+
+def _act(rs, n, c, h, w, dtype, scale=1.0):
+    x = (rs.standard_normal((n, c, h, w)) * scale).astype(np.float32)
+    xq = bf16_round(x) if dtype == torch.bfloat16 else x.astype(np.float64)
+    return to_nhwc(x, dtype), xq
+
+
+def _tol(dtype):
+    return (2.0 ** -8, 2e-3) if dtype == torch.bfloat16 else (1e-5, 1e-5)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+@pytest.mark.parametrize('shape', [(1, 16, 8), (2, 19, 13), (1, 5, 3), (3, 48, 48), (1, 33, 70)])
+@pytest.mark.parametrize('simt', [False, True])
+def test_conv48_plain(prec, shape, simt):
+    dtype = DT[prec]
+    if prec == 'fp32' and simt:
+        pytest.skip('fp32 is always the CUDA-core kernel')
+    n, h, w = shape
+    rs = np.random.RandomState(1000 * shape[0] + 31 * shape[1] + shape[2])
+    wt, b, wq = _rand_conv(rs, 48, 48, dtype)
+    x, xq = _act(rs, n, 48, h, w, dtype)
+    packed = _pack(wt, dtype, 48)
+    out = torch.empty_like(x)
+    ops.conv3x3([x], packed, 48, bias=torch.from_numpy(b).cuda(), out=out, simt=simt)
+    torch.cuda.synchronize()
+    ref = O.conv2d(xq, wq, b.astype(np.float64))
+    rtol, atol = _tol(dtype)
+    np.testing.assert_allclose(from_nhwc(out), ref, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+def test_conv48_epilogue_relu_mask_residuals(prec):
+    dtype = DT[prec]
+    n, h, w = 2, 21, 11
+    rs = np.random.RandomState(7)
+    wt, b, wq = _rand_conv(rs, 48, 48, dtype)
+    x, xq = _act(rs, n, 48, h, w, dtype)
+    r1, r1q = _act(rs, n, 48, h, w, dtype)
+    r2, r2q = _act(rs, n, 48, h, w, dtype)
+    mk, mkq = _act(rs, n, 48, h, w, dtype)
+    packed = _pack(wt, dtype, 48)
+    bt = torch.from_numpy(b).cuda()
+    rtol, atol = _tol(dtype)
+    conv = O.conv2d(xq, wq, b.astype(np.float64))
+    # relu + two residuals (ResidualBlock conv2 with the LarvaBody skip folded in)
+    out = torch.empty_like(x)
+    ops.conv3x3([x], packed, 48, bias=bt, out=out, relu=True, res1=r1, res2=r2)
+    np.testing.assert_allclose(from_nhwc(out), np.maximum(conv, 0) + r1q + r2q, rtol=rtol, atol=atol)
+    # mask + residual, no bias (backward-data epilogue)
+    out2 = torch.empty_like(x)
+    ops.conv3x3([x], packed, 48, bias=None, out=out2, mask=mk, res1=r1)
+    ref2 = O.conv2d(xq, wq) * (mkq > 0) + r1q
+    np.testing.assert_allclose(from_nhwc(out2), ref2, rtol=rtol, atol=atol)
+    # in-place accumulate: out aliases res1
+    acc = r1.clone()
+    ops.conv3x3([x], packed, 48, bias=None, out=acc, res1=acc)
+    np.testing.assert_allclose(from_nhwc(acc), O.conv2d(xq, wq) + r1q, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+def test_conv_pixelshuffle_base_loss(prec):
+    dtype = DT[prec]
+    n, h, w = 2, 18, 9
+    rs = np.random.RandomState(11)
+    wt, b, wq = _rand_conv(rs, 48, 48, dtype, wscale=0.3)
+    x, xq = _act(rs, n, 48, h, w, dtype)
+    base = (rs.uniform(0, 255, (n, 3, 4 * h, 4 * w))).astype(np.float32)
+    truth = (rs.uniform(0, 255, (n, 3, 4 * h, 4 * w))).astype(np.float32)
+    packed = _pack(wt, dtype, 48)
+    out_hr = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    g = torch.empty_like(x)
+    ops.conv3x3([x], packed, 48, bias=torch.from_numpy(b).cuda(), epilogue=_lib.LV_EPI_PS4_NCHW, out_hr=out_hr,
+                base_hr=torch.from_numpy(base).cuda(), truth_hr=torch.from_numpy(truth).cuda(), loss_sum=loss, grad_sign=g)
+    ref = O.pixel_shuffle(O.conv2d(xq, wq, b.astype(np.float64)), 4) + base
+    got = out_hr.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got, ref, rtol=2e-6, atol=2e-3 if prec == 'bf16' else 2e-4)
+    # loss / sign gradient must be consistent with the kernel's own fp32 output
+    assert abs(loss.item() - np.abs(got - truth).sum()) <= 1e-6 * np.abs(got - truth).sum()
+    gref = O.pixel_unshuffle(np.sign(got - truth.astype(np.float64)), 4)
+    np.testing.assert_array_equal(from_nhwc(g), gref)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+@pytest.mark.parametrize('nsrc', [2, 4])
+def test_conv_multi_source_merge(prec, nsrc):
+    dtype = DT[prec]
+    n, h, w = 1, 17, 20
+    rs = np.random.RandomState(13 + nsrc)
+    wt, b, wq = _rand_conv(rs, 48, 48 * nsrc, dtype)
+    srcs, srcq = zip(*[_act(rs, n, 48, h, w, dtype) for _ in range(nsrc)])
+    packed = _pack(wt, dtype, 48)
+    out = torch.empty_like(srcs[0])
+    ops.conv3x3(list(srcs), packed, 48, bias=torch.from_numpy(b).cuda(), out=out)
+    ref = O.conv2d(np.concatenate(srcq, axis=1), wq, b.astype(np.float64))
+    rtol, atol = _tol(dtype)
+    np.testing.assert_allclose(from_nhwc(out), ref, rtol=rtol, atol=atol * 2)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+def test_dgrad_operand(prec):
+    """conv with the transposed/rotated packed operand == oracle conv2d_backward wrt the input."""
+    dtype = DT[prec]
+    n, h, w = 2, 16, 12
+    rs = np.random.RandomState(17)
+    wt, _, wq = _rand_conv(rs, 48, 96, dtype)
+    dy, dyq = _act(rs, n, 48, h, w, dtype)
+    x_dummy = np.zeros((n, 96, h, w))
+    dx_ref, _, _ = O.conv2d_backward(x_dummy, wq, dyq)
+    rtol, atol = _tol(dtype)
+    for s in range(2):
+        packed = _pack(wt, dtype, 48, transpose=1, i_off=48 * s, i_cnt=48)
+        out = torch.empty_like(dy)
+        ops.conv3x3([dy], packed, 48, bias=None, out=out)
+        np.testing.assert_allclose(from_nhwc(out), dx_ref[:, 48 * s:48 * (s + 1)], rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+def test_head_and_bicubic(prec):
+    dtype = DT[prec]
+    n, h, w = 2, 37, 21
+    rs = np.random.RandomState(19)
+    x = rs.uniform(0, 255, (n, 3, h, w)).astype(np.float32)
+    wt = (rs.standard_normal((48, 3, 3, 3)) * 0.05).astype(np.float32)
+    b = (rs.standard_normal(48) * 0.5).astype(np.float32)
+    fea = torch.empty((n, h, w, 48), dtype=dtype, device='cuda')
+    base = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device='cuda')
+    ops.head_bicubic(torch.from_numpy(x).cuda(), torch.from_numpy(wt).cuda(), torch.from_numpy(b).cuda(), fea, base)
+    ref = O.conv2d(x.astype(np.float64), wt.astype(np.float64), b.astype(np.float64))
+    rtol, atol = _tol(dtype)
+    np.testing.assert_allclose(from_nhwc(fea), ref, rtol=rtol, atol=max(atol, 1e-3))
+    bref = O.bicubic_upsample(x.astype(np.float64), 4)
+    np.testing.assert_allclose(base.cpu().numpy(), bref, rtol=0, atol=2e-4)
+    out2 = torch.empty_like(base)
+    ops.bicubic_x4(torch.from_numpy(x).cuda(), out2)
+    assert torch.equal(out2, base)
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+@pytest.mark.parametrize('simt', [False, True])
+def test_wgrad(prec, simt):
+    dtype = DT[prec]
+    if prec == 'fp32' and simt:
+        pytest.skip('fp32 is always the CUDA-core kernel')
+    n, h, w = 2, 23, 19
+    rs = np.random.RandomState(23)
+    x, xq = _act(rs, n, 48, h, w, dtype)
+    dy, dyq = _act(rs, n, 48, h, w, dtype)
+    dw = torch.zeros((48, 48, 3, 3), dtype=torch.float32, device='cuda')
+    db = torch.zeros(48, dtype=torch.float32, device='cuda')
+    batch = ops.WgradBatch([dict(x=x, dy=dy, dw=dw, db=db, scale=0.5)], splits=5, device='cuda')
+    batch.launch(simt=simt)
+    batch.launch(simt=simt)  # accumulates: second launch doubles the result
+    _, dw_ref, db_ref = O.conv2d_backward(xq, np.zeros((48, 48, 3, 3)), dyq)
+    assert rel_l2(dw.cpu().numpy(), dw_ref) < 1e-5
+    assert rel_l2(db.cpu().numpy(), db_ref) < 1e-5
+
+
+@pytest.mark.parametrize('prec', ['bf16', 'fp32'])
+def test_wgrad_merge_slices_and_head(prec):
+    dtype = DT[prec]
+    n, h, w = 1, 16, 24
+    rs = np.random.RandomState(29)
+    xs, xq = zip(*[_act(rs, n, 48, h, w, dtype) for _ in range(2)])
+    dy, dyq = _act(rs, n, 48, h, w, dtype)
+    dw = torch.zeros((48, 96, 3, 3), dtype=torch.float32, device='cuda')
+    db = torch.zeros(48, dtype=torch.float32, device='cuda')
+    items = [dict(x=xs[s], dy=dy, dw=dw, db=db if s == 0 else None, cin_total=96, cin_off=48 * s) for s in range(2)]
+    ops.WgradBatch(items, splits=3, device='cuda').launch()
+    _, dw_ref, db_ref = O.conv2d_backward(np.concatenate(xq, 1), np.zeros((48, 96, 3, 3)), dyq)
+    assert rel_l2(dw.cpu().numpy(), dw_ref) < 1e-5
+    assert rel_l2(db.cpu().numpy(), db_ref) < 1e-5
+    # head weight gradient (fp32 image input)
+    img = rs.uniform(0, 255, (n, 3, h, w)).astype(np.float32)
+    dwh = torch.zeros((48, 3, 3, 3), dtype=torch.float32, device='cuda')
+    dbh = torch.zeros(48, dtype=torch.float32, device='cuda')
+    ops.head_wgrad(torch.from_numpy(img).cuda(), dy, dwh, dbh, 0.25)
+    _, dwh_ref, dbh_ref = O.conv2d_backward(img.astype(np.float64), np.zeros((48, 3, 3, 3)), dyq)
+    assert rel_l2(dwh.cpu().numpy(), 0.25 * dwh_ref) < 1e-5
+    assert rel_l2(dbh.cpu().numpy(), 0.25 * dbh_ref) < 1e-5
+
+
+def test_layout_loss_adamw_helpers():
+    rs = np.random.RandomState(31)
+    x = rs.standard_normal((2, 48, 7, 5)).astype(np.float32)
+    for dtype in (torch.float32, torch.bfloat16):
+        a = torch.empty((2, 7, 5, 48), dtype=dtype, device='cuda')
+        ops.nchw_to_nhwc(torch.from_numpy(x).cuda(), a)
+        back = torch.empty((2, 48, 7, 5), dtype=torch.float32, device='cuda')
+        ops.nhwc_to_nchw(a, back)
+        ref = bf16_round(x) if dtype == torch.bfloat16 else x
+        np.testing.assert_array_equal(back.cpu().numpy(), ref.astype(np.float32))
+    out = rs.uniform(0, 255, (2, 3, 16, 12)).astype(np.float32)
+    truth = rs.uniform(0, 255, (2, 3, 16, 12)).astype(np.float32)
+    truth[0, 0, 0, 0] = out[0, 0, 0, 0]  # sign(0) == 0
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    g = torch.empty((2, 4, 3, 48), dtype=torch.bfloat16, device='cuda')
+    ops.l1_loss_grad(torch.from_numpy(out).cuda(), torch.from_numpy(truth).cuda(), loss, g)
+    assert abs(loss.item() - np.abs(out.astype(np.float64) - truth).sum()) < 1e-3
+    np.testing.assert_array_equal(from_nhwc(g), O.pixel_unshuffle(np.sign(out.astype(np.float64) - truth), 4))
+    # AdamW, 3 steps vs the oracle restatement of torch.optim.AdamW
+    p0 = rs.standard_normal(1000).astype(np.float32)
+    p = torch.from_numpy(p0.copy()).cuda()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pr, mr, vr = p0.astype(np.float64), np.zeros(1000), np.zeros(1000)
+    for step in range(1, 4):
+        gnp = rs.standard_normal(1000).astype(np.float32)
+        ops.adamw_step(p, torch.from_numpy(gnp).cuda(), m, v, 4e-4, 0.9, 0.999, 1e-8, 0.01, step)
+        pr, mr, vr = O.adamw_step(pr, gnp.astype(np.float64), mr, vr, step, 4e-4)
+    np.testing.assert_allclose(p.cpu().numpy(), pr, rtol=1e-5, atol=1e-6)
+
+
+def test_errors_are_loud():
+    x = torch.zeros((1, 8, 8, 40), dtype=torch.bfloat16, device='cuda')
+    with pytest.raises(_lib.LarvaNetB200Error):
+        ops.conv3x3([x], torch.zeros(16, dtype=torch.uint8, device='cuda'), 48, out=torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device='cuda'))
+    with pytest.raises(_lib.LarvaNetB200Error):
+        ops.conv3x3([x.cpu()], torch.zeros(16, dtype=torch.uint8), 48, out=x.cpu())

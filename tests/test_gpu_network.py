@@ -1,0 +1,215 @@
+"""Network-level parity (`-m gpu`): the drop-in LarvaNet / LarvaNetV2 plugins against the committed golden outputs
+of the reference modules and against the numpy oracle, in both precision modes.
+
+Tolerances (north star): bf16 -- max |err| <= 2.0 on the 0..255 output and PSNR delta <= 0.01 dB;
+fp32 validation mode -- <= 1e-4 relative.  Gradients: rel-L2 <= 2e-2 (bf16) / 1e-4 (fp32) per parameter tensor.
+"""
+import importlib
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from larvanet_b200 import synth
+from oracle import larva_oracle as O
+from tests.gpu_util import load_params, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+LARVA_CASES = ['larvanet_m2_b21', 'larvanet_m3_b111', 'larvanetv2_m2_b11', 'larvanetv2_m4_b1111']
+
+
+def _make(v2, blocks, precision, training=False):
+    mod = importlib.import_module('models.LarvaNetV2' if v2 else 'models.LarvaNet')
+    m = mod.create_model()
+    m.parse_args([f'--num_modules={len(blocks)}', '--num_blocks=' + ','.join(map(str, blocks)), f'--precision={precision}'])
+    m.prepare(is_training=training, scales=[4])
+    return m
+
+
+def _case(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    v2 = bool(g['v2'])
+    blocks = [int(b) for b in g['blocks']]
+    params = synth.make_larva_params(blocks, v2=v2, seed=int(g['seed']), bias_std=0.02)
+    lr, hr = synth.make_images(int(g['n']), int(g['h']), int(g['w']), seed=int(g['seed']) + 100)
+    return g, v2, blocks, params, lr, hr
+
+
+@pytest.mark.parametrize('name', LARVA_CASES)
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_inference_matches_reference_golden(golden_dir, name, precision):
+    g, v2, blocks, params, lr, hr = _case(golden_dir, name)
+    m = _make(v2, blocks, precision)
+    load_params(m.get_model(), params)
+    out = m.upscale(list(lr), 4)
+    ref = g['out_f32']
+    assert out.shape == ref.shape and out.dtype == np.float32
+    if precision == 'fp32':
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4 * 255)
+    else:
+        assert np.max(np.abs(out - ref)) <= 2.0
+        p_ref = O.image_psnr(O.image_to_uint8(ref), O.image_to_uint8(hr))
+        p_out = O.image_psnr(O.image_to_uint8(out), O.image_to_uint8(hr))
+        assert abs(p_ref - p_out) <= 0.01
+    # second call with the same input replays the CUDA graph and must give identical bits
+    out2 = m.upscale(list(lr), 4)
+    np.testing.assert_array_equal(out, out2)
+
+
+@pytest.mark.parametrize('name', LARVA_CASES)
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_train_step_loss_and_grads(golden_dir, name, precision):
+    g, v2, blocks, params, lr, hr = _case(golden_dir, name)
+    m = _make(v2, blocks, precision, training=True)
+    load_params(m.get_model(), params)
+    eng = m._engine()
+    x = torch.from_numpy(lr).cuda()
+    t = torch.from_numpy(hr).cuda()
+    loss = eng.train_step(x, t, keep_exits=True).item()
+    ref_loss, ref_grads, ref_outs = O.larvanet_train_step(params, lr, hr, blocks, v2=v2)
+    assert abs(ref_loss - float(g['loss_f32'])) < 1e-5 * ref_loss   # oracle is pinned to the reference
+    ltol, gtol = (1e-5, 1e-4) if precision == 'fp32' else (2e-3, 2e-2)
+    assert abs(loss - ref_loss) <= ltol * ref_loss
+    for k, e in enumerate(eng.last_exits):
+        err = np.max(np.abs(e.cpu().numpy() - ref_outs[k]))
+        assert err <= (1e-4 * 255 if precision == 'fp32' else 2.0)
+    # The L1 gradient sign(out - truth) is discontinuous: where |out - truth| is below the forward error the sign
+    # flips, and a fraction f of flipped signs alone moves the gradient by 2*sqrt(f) in relative L2.  The backward
+    # kernels are therefore checked against the oracle's backward driven by the DEVICE's exit outputs (same signs),
+    # and the end-to-end gradient against the pure oracle with the flip budget added.
+    dev_exits = [e.cpu().numpy() for e in eng.last_exits]
+    _, same_sign_grads, _ = O.larvanet_train_step(params, lr, hr, blocks, v2=v2, sign_from=dev_exits)
+    flips = np.mean([np.mean(np.sign(d - hr) != np.sign(r - hr)) for d, r in zip(dev_exits, ref_outs)])
+    for name_, p in m.get_model().named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape
+        got = p.grad.cpu().numpy()
+        r = rel_l2(got, same_sign_grads[name_])
+        assert r <= gtol, (name_, r)
+        r2 = rel_l2(got, ref_grads[name_])
+        assert r2 <= gtol + 4.0 * np.sqrt(flips), (name_, r2, flips)
+    if precision == 'bf16':
+        # replay (CUDA graph) reproduces the same conv gradients bit for bit (deterministic split-K reduction);
+        # the head gradient uses fp32 atomics and is excluded, as is the fp32 validation mode (atomics throughout)
+        g1 = eng.arena.grad.clone()
+        eng.train_step(x, t, keep_exits=True)
+        lo, hi = eng.arena.slice_of('body_')
+        assert torch.equal(g1[lo:hi], eng.arena.grad[lo:hi])
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_plugin_train_step_updates_like_adamw(precision):
+    """train_step_larva == fwd/bwd + AdamW: compare the updated weights with the oracle's AdamW on oracle grads."""
+    blocks = [1, 1]
+    params = synth.make_larva_params(blocks, seed=5, bias_std=0.02)
+    lr_img, hr_img = synth.make_smooth_images(2, 16, 16, seed=6)
+    m = _make(False, blocks, precision, training=True)
+    load_params(m.get_model(), params)
+    m.volume_per_step = 1
+    m.args.val_volume = 1e30
+    m.global_step = 5            # != 0 so step 1's validation hook (needs a val loader) is skipped
+    args = types.SimpleNamespace(train_path='/tmp')
+    loss = m.train_step_larva(args, None, torch.from_numpy(lr_img).cuda(), torch.from_numpy(hr_img).cuda())
+    ref_loss, ref_grads, _ = O.larvanet_train_step(params, lr_img, hr_img, blocks)
+    assert abs(loss - ref_loss) <= (1e-5 if precision == 'fp32' else 2e-3) * ref_loss
+    sd = m.get_model().state_dict()
+    for k in params:
+        newp, _, _ = O.adamw_step(params[k].astype(np.float64), ref_grads[k], 0.0, 0.0, 1, m.args.lr)
+        # first AdamW step moves every weight by ~lr*sign(grad): compare the update direction/magnitude
+        upd = sd[k].cpu().numpy().astype(np.float64) - params[k]
+        ref_upd = newp - params[k]
+        # step 1 of AdamW moves a weight by ~ -lr*sign(grad): only elements whose gradient is clearly non-zero
+        # have a well-defined direction
+        sel = np.abs(ref_grads[k]) > 1e-3 * np.abs(ref_grads[k]).max()
+        agree = np.mean(np.sign(upd[sel]) == np.sign(ref_upd[sel]))
+        assert agree > (0.995 if precision == 'fp32' else 0.97), (k, agree)
+    # weights changed -> packed operands must be refreshed: a second step must not reuse stale weights
+    out_a = m.upscale(list(lr_img), 4)
+    ref_a = O.larvanet_forward({k: v.cpu().numpy() for k, v in sd.items()}, lr_img, blocks)
+    assert np.max(np.abs(out_a - ref_a)) <= (1e-4 * 255 if precision == 'fp32' else 2.0)
+
+
+def test_known_answer_invariants():
+    blocks = [2, 2]
+    m = _make(False, blocks, 'bf16')
+    mod = m.get_model()
+    # (i) all-zero conv weights => output == bicubic base exactly (reference models/LarvaNet.py:263-267)
+    zero = {k: np.zeros(s, np.float32) for k, s in synth.larva_param_shapes(blocks).items()}
+    load_params(mod, zero)
+    lr, _ = synth.make_images(1, 40, 24, seed=3)
+    x = torch.from_numpy(lr).cuda()
+    out = mod(x)
+    base = mod.base(x)
+    assert torch.equal(out, base)
+    np.testing.assert_allclose(base.cpu().numpy(), O.bicubic_upsample(lr.astype(np.float64)), atol=2e-4)
+    # (iv) state_dict key/shape equality with the reference layout, and checkpoint round trip
+    sd = mod.state_dict()
+    shapes = synth.larva_param_shapes(blocks)
+    assert list(sd.keys()) == list(shapes.keys())
+    assert all(tuple(sd[k].shape) == shapes[k] and sd[k].dtype == torch.float32 for k in shapes)
+
+
+def test_module_level_calls_match_fused_forward(golden_dir):
+    """head/base/body_i/leg called one by one (reference models/LarvaNet.py:102-107 style) == fused forward."""
+    g, v2, blocks, params, lr, hr = _case(golden_dir, 'larvanet_m2_b21')
+    m = _make(False, blocks, 'fp32')
+    mod = m.get_model()
+    load_params(mod, params)
+    x = torch.from_numpy(lr).cuda()
+    fea = mod.head(x)
+    np.testing.assert_allclose(fea.cpu().numpy(), g['head_f32'], rtol=1e-4, atol=1e-3)
+    base = mod.base(x)
+    for i in range(len(blocks)):
+        fea = getattr(mod, f'body_{i}')(fea)
+        out = getattr(mod, f'body_{i}').leg(fea, base)
+        np.testing.assert_allclose(out.cpu().numpy(), g['exits_f32'][i], rtol=1e-4, atol=1e-4 * 255)
+    np.testing.assert_allclose(fea.cpu().numpy(), g['feat_last_f32'], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(mod(x).cpu().numpy(), out.cpu().numpy(), rtol=1e-6, atol=1e-4)
+
+
+def test_early_exit_matches_reference(golden_dir):
+    g, v2, blocks, params, lr, hr = _case(golden_dir, 'larvanet_m3_b111')
+    m = _make(False, blocks, 'fp32')
+    load_params(m.get_model(), params)
+    eng = m._engine()
+    x = torch.from_numpy(lr).cuda()
+    for k in range(len(blocks) + 1):
+        out = eng.forward(x, exit_leg=k).cpu().numpy()
+        np.testing.assert_allclose(out, g[f'exit_leg{k}_f32'], rtol=1e-4, atol=1e-4 * 255)
+
+
+@pytest.mark.parametrize('shape', [(1, 180, 320), (4, 48, 48)])
+def test_tensor_core_path_equals_cuda_core_path_at_full_size(shape):
+    """BASELINE config sizes: the tcgen05 chain vs the CUDA-core chain on identical bf16 operands (size-independent
+    cross-check; the CPU oracle is too slow here)."""
+    n, h, w = shape
+    blocks = [4, 4, 4, 4]
+    params = synth.make_larva_params(blocks, seed=0)
+    lr, hr = synth.make_images(n, h, w, seed=1, quantize=True)
+    m = _make(False, blocks, 'bf16')
+    load_params(m.get_model(), params)
+    eng = m._engine()
+    x = torch.from_numpy(lr).cuda()
+    a = eng.forward(x).clone()
+    eng.simt = True
+    b = eng.forward(x).clone()
+    eng.simt = False
+    assert torch.isfinite(a).all()
+    # identical operands; fp32 accumulation order differs -> rare 1-ulp bf16 flips upstream, tiny on the output
+    assert (a - b).abs().max().item() <= 0.05
+
+
+def test_empty_and_ragged_inputs():
+    blocks = [1, 1]
+    m = _make(False, blocks, 'bf16')
+    load_params(m.get_model(), synth.make_larva_params(blocks, seed=2))
+    eng = m._engine()
+    for shape in [(1, 1, 1), (1, 3, 50), (2, 17, 9)]:
+        lr, _ = synth.make_images(*shape, seed=4)
+        out = eng.forward(torch.from_numpy(lr).cuda()).cpu().numpy()
+        ref = O.larvanet_forward({k: v for k, v in synth.make_larva_params(blocks, seed=2).items()}, lr, blocks)
+        assert np.max(np.abs(out - ref)) <= 2.0
+    out = eng.forward(torch.zeros((0, 3, 8, 8), device='cuda'))
+    assert out.shape == (0, 3, 32, 32)
