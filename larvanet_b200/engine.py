@@ -20,7 +20,7 @@ import os
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import LV_EPI_NHWC, LV_EPI_PS4_NCHW, LarvaNetB200Error
 
 C = 48  # LarvaNet feature width (reference models/LarvaNet.py:226 -- hard-wired)
@@ -101,6 +101,7 @@ class LarvaEngine:
         self._infer = {}   # shape -> (bufs, graph)
         self._train = {}
         self.simt = False  # tests flip this to cross-check the tensor-core kernels on CUDA cores
+        self.replayed_launches = 0  # kernels executed through CUDA-graph replays (lv_launch_count only sees eager ones)
         # data parallel
         self.world_size = 1
         self.process_group = None
@@ -235,10 +236,13 @@ class LarvaEngine:
                 self._run_infer(b, exit_leg)  # warm-up (also sets func attributes outside capture)
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
+                c0 = _lib.launch_count()
                 with torch.cuda.graph(g):
                     self._run_infer(b, exit_leg)
                 ent[1] = g
+                ent.append(_lib.launch_count() - c0)
             ent[1].replay()
+            self.replayed_launches += ent[2]
         else:
             self._run_infer(b, exit_leg)
         return b.out
@@ -389,10 +393,13 @@ class LarvaEngine:
                 self._run_train(b)
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
+                c0 = _lib.launch_count()
                 with torch.cuda.graph(g):
                     self._run_train(b)
                 ent[1] = g
+                ent.append(_lib.launch_count() - c0)
             ent[1].replay()
+            self.replayed_launches += ent[2]
         else:
             self._run_train(b)
         if self.world_size > 1:

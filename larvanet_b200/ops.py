@@ -105,8 +105,21 @@ def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res
     return a
 
 
+# bench.py's instrumented pass: when a list is installed here every conv launch is bracketed by CUDA events on the
+# launching stream and (event0, event1, flops, tag) is appended
+CONV_TIMERS = None
+
+
 def conv3x3_launch(args, max_ctas=0, simt=False):
     lib = _lib.load()
+    if CONV_TIMERS is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.lv_conv3x3(C.byref(args), int(max_ctas), _stream()), 'lv_conv3x3')
+        e1.record()
+        flops = 2.0 * 9 * args.cin * args.num_src * args.cout * args.n * args.h * args.w
+        CONV_TIMERS.append((e0, e1, flops, (args.cin * args.num_src, args.cout, args.epilogue)))
+        return
     if simt:
         check(lib.lv_conv3x3_simt(C.byref(args), _stream()), 'lv_conv3x3_simt')
     else:

@@ -118,3 +118,20 @@ def test_conv_backward_matches_finite_difference():
         num = ((O.conv2d(x, wp) - O.conv2d(x, w)) * dy).sum() / eps
         assert abs(num - dw[idx]) < 1e-4
     np.testing.assert_allclose(db, dy.sum((0, 2, 3)))
+
+
+@pytest.mark.parametrize('name', ['larvanet_m2_b21', 'larvanetv2_m2_b11'])
+def test_torch_cpu_port_matches_golden(golden_dir, name):
+    """The timed CPU baseline (oracle/torch_port.py) computes the same function as the reference modules."""
+    import torch
+    from oracle import torch_port
+    g = _load(golden_dir, name)
+    v2 = bool(g['v2'])
+    blocks = [int(b) for b in g['blocks']]
+    params = synth.make_larva_params(blocks, v2=v2, seed=int(g['seed']), bias_std=0.02)
+    lr, hr = synth.make_images(int(g['n']), int(g['h']), int(g['w']), seed=int(g['seed']) + 100)
+    tr = torch_port.CpuTrainer(params, blocks, v2=v2, threads=2)
+    out = tr.infer(torch.from_numpy(lr)).numpy()
+    np.testing.assert_allclose(out, g['out_f32'], rtol=1e-5, atol=1e-3)
+    loss = torch_port.loss_fn(tr.p, torch.from_numpy(lr), torch.from_numpy(hr), blocks, v2).item()
+    assert abs(loss - float(g['loss_f32'])) <= 1e-5 * loss
