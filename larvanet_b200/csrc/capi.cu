@@ -36,6 +36,7 @@ int sm_count() {
 int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
 int conv3x3_simt(const lv_conv_args& a, cudaStream_t stream);
 int pick_ntile(int cout_pad);
+extern long long* g_timeline;
 int head_bicubic_fwd(const float*, const float*, const float*, const float*, const float*, void*, float*, int, int, int, int,
                      int, cudaStream_t);
 int bicubic_x4(const float*, float*, int, int, int, int, cudaStream_t);
@@ -89,6 +90,9 @@ extern "C" {
 const char* lv_last_error(void) { return g_err; }
 int lv_abi_version(void) { return LV_ABI_VERSION; }
 int64_t lv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+// developer hook (not in the public header): device buffer of 3*64*4 int64 that CTA 0 of the next tensor-core conv
+// launches fills with clock64 stamps per role/tile; pass NULL to switch off
+void lv_debug_set_timeline(long long* buf) { lv::g_timeline = buf; }
 
 int lv_device_check(int dev, int* sm) {
   cudaDeviceProp prop;

@@ -16,8 +16,14 @@ struct ConvGeom {
   int tiles_x, tiles_y, ntiles_n;  // pixel tiles per image in x / y, N tiles
   int nt;                          // output channels per N tile
   int cout_pad;                    // cout rounded up to 16
-  long long total_tiles;
+  int total_tiles;
+  long long* timeline;             // debug: per-role clock64 stamps of CTA 0 (nullptr in production)
 };
+
+// debug timeline record: [role][slot] = clock64; role 0 producer, 1 mma, 2 epilogue; 4 stamps per tile
+__device__ __forceinline__ void tl_stamp(const ConvGeom& g, int role, uint32_t tile_k, int ev) {
+  if (g.timeline != nullptr && blockIdx.x == 0 && tile_k < 64) g.timeline[(role * 64 + tile_k) * 4 + ev] = clock64();
+}
 
 template <typename T>
 __device__ __forceinline__ float conv_epilogue16(const lv_conv_args& a, int n, int y, int x, int co0, float* v) {

@@ -6,14 +6,23 @@
 // staged in shared memory ONCE, channel-chunk-planar: [chunk of 8 channels][halo pixel][16 B].  That is exactly the
 // SWIZZLE_NONE K-major UMMA operand layout with "8-row group" = one tile row, so the A operand of tap (ky,kx) is
 // the same buffer with the descriptor start address moved by (ky*10+kx)*16 bytes and SBO = 160 B (halo row pitch):
-// no im2col, no per-tap copies, zero padding comes from zero-filled halo pixels.
+// no im2col, no per-tap copies, zero padding comes from zero-filled halo pixels.  (Measured on B200: the cost of one
+// M=128,K=16 SS MMA is max(N/2, 32+N/4) cycles and does NOT depend on swizzle mode or operand alignment.)
 //
 // Weights (bf16, pre-packed as [ntile][src][tap][chunk][cout][8]) stay resident in shared memory for the whole
 // persistent CTA; they arrive with one TMA bulk copy per (src,tap) block.
 //
-// Warp roles (288 threads): warps 0-3 epilogue (one TMEM lane quarter each), warp 4 TMEM alloc + single-thread
-// MMA issue, warps 5-8 halo-tile producers (cp.async 16 B, zero-fill outside the image).  Two TMEM accumulator
-// stages let the epilogue of tile i overlap the MMAs of tile i+1; NSTAGE halo stages decouple loads from MMAs.
+// Warp roles (416 threads): warps 0-3 = epilogue group 0, warps 4-7 = epilogue group 1 (warp w reads TMEM lane quarter
+// w%4), warp 8 TMEM alloc + MMA issue by one elected lane, warps 9-12 halo-tile producers (cp.async 16 B, zero-fill
+// outside the image).  The CTA's tiles alternate between the two TMEM accumulator stages; stage s is always drained by
+// epilogue group s, so two epilogues and one MMA phase are in flight at any time.
+//
+// Shared memory bandwidth is the bounding resource of this kernel (measured: one M=128,N=48,K=16 SS MMA = 45 cycles =
+// its 5.5 KB of operand reads at 128 B/clk), so everything else is arranged to stay out of its way:
+// Epilogue (NHWC outputs): each group prefetches the residual / skip / ReLU-mask tile of its NEXT tile with cp.async
+// while the MMAs run, adds bias/ReLU/mask/residuals in registers, stages the bf16 tile as dense NHWC rows in shared
+// memory and copies it out with fully coalesced 16 B stores -- no epilogue thread waits on global memory.
+// PixelShuffle / RGB epilogues keep the direct per-thread path (their stores are already full 128 B lines).
 #include "conv_epilogue.cuh"
 #include "lv_common.cuh"
 
@@ -21,27 +30,38 @@ namespace lv {
 
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2, kHaloPix = kHaloW * kHaloH;  // 10 x 18 = 180
-constexpr int kEpiThreads = 128, kProdThreads = 128;
-constexpr int kTcThreads = kEpiThreads + 32 + kProdThreads;  // 288
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 128;
+constexpr int kMmaWarp = kEpiWarps;                           // warp 8
+constexpr int kTcThreads = kEpiThreads + 32 + kProdThreads;  // 416
+constexpr int kMaxRes = 3;                                    // mask, res1, res2
 
 template <int CIN, int NT, int NSTAGE>
 struct TcCfg {
   static constexpr int CH = CIN / 8;                    // 16-byte channel chunks per pixel
   static constexpr int KSTEPS = CIN / 16;               // UMMA K steps per tap
-  static constexpr int A_PLANE = kHaloPix * 16;         // bytes of one chunk plane
+  static constexpr int A_PLANE = kHaloPix * 16 + 16;    // bytes of one chunk plane (+16: spreads cp.async banks)
   static constexpr int A_STAGE = CH * A_PLANE;
   static constexpr int W_TAP = CH * NT * 16;            // bytes of one (src,tap) weight block
   static constexpr int ACC_STRIDE = (NT <= 64) ? 64 : 128;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static constexpr int LAG = (NSTAGE >= 3) ? 2 : 1;     // cp.async groups kept in flight per producer thread
-  static size_t smem_bytes(int num_src) {
-    return static_cast<size_t>(num_src) * 9 * W_TAP + static_cast<size_t>(NSTAGE) * A_STAGE + 256;
+  static constexpr int PIX_PITCH = NT * 2 + 16;         // staged pixel pitch (+16 B: conflict-free 16 B accesses)
+  static constexpr int OUT_TILE = 128 * PIX_PITCH;      // bytes of one staged NHWC tile (bf16)
+  static constexpr int PROD_PIECES = (kHaloPix * CH + kProdThreads - 1) / kProdThreads;
+  static size_t smem_bytes(int num_src, int staged, int nres, int cout_pad) {
+    return static_cast<size_t>(num_src) * 9 * W_TAP + static_cast<size_t>(NSTAGE) * A_STAGE +
+           (staged ? static_cast<size_t>(2) * (1 + nres) * OUT_TILE : 0) + static_cast<size_t>(cout_pad) * 4 + 256;
   }
 };
 
+struct TcLaunch {
+  int staged;  // NHWC epilogue through shared memory + TMA bulk stores
+  int nres;    // number of prefetched epilogue inputs (mask, res1, res2 in that order)
+};
+
 template <int CIN, int NT, int NSTAGE>
-__global__ void __launch_bounds__(kTcThreads, (CIN == 48 && NT == 48) ? 2 : 1)
-conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, const TcLaunch L) {
   using Cfg = TcCfg<CIN, NT, NSTAGE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -49,8 +69,11 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
 
   const uint32_t w_bytes = static_cast<uint32_t>(a.num_src) * 9u * Cfg::W_TAP;
   uint8_t* sW = smem;
-  uint8_t* sA = smem + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NSTAGE * Cfg::A_STAGE);
+  uint8_t* sA = sW + w_bytes;
+  uint8_t* sEpi = sA + NSTAGE * Cfg::A_STAGE;  // per epilogue group: [out tile][nres residual tiles]
+  const int epi_bytes = L.staged ? (1 + L.nres) * Cfg::OUT_TILE : 0;
+  float* sBias = reinterpret_cast<float*>(sEpi + 2 * epi_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + g.cout_pad);
   // bars: [0,NSTAGE) full, [NSTAGE,2NSTAGE) empty, then tmem_full[2], tmem_empty[2], wbar
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -67,12 +90,14 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiThreads);
+      mbar_init(tempty_bar(s), kEpiThreads / 2);
     }
     mbar_init(wbar, 1);
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  for (int i = threadIdx.x; i < g.cout_pad; i += kTcThreads)
+    sBias[i] = (a.bias != nullptr && i < a.cout) ? a.bias[i] : 0.f;
+  if (warp == kMmaWarp) tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -81,46 +106,73 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
   const int ntile = static_cast<int>(blockIdx.x % g.ntiles_n);  // fixed per CTA (grid is a multiple of ntiles_n)
   const int tiles_per_img = g.tiles_x * g.tiles_y;
 
-  if (warp >= 5) {
+  if (warp > kMmaWarp) {
     // =============================== producers: halo tiles -> smem ===============================
     const int ptid = threadIdx.x - (kEpiThreads + 32);
+    // tile-invariant description of this thread's 16 B pieces of a halo tile
+    uint32_t pc_dst[Cfg::PROD_PIECES];   // smem offset inside a stage
+    int pc_rel[Cfg::PROD_PIECES];        // element offset relative to the halo origin pixel
+    int pc_rc[Cfg::PROD_PIECES];         // (row << 8) | col inside the halo, -1 = no piece
+#pragma unroll
+    for (int i = 0; i < Cfg::PROD_PIECES; ++i) {
+      const int idx = ptid + i * kProdThreads;
+      const int p = idx / Cfg::CH, c = idx - p * Cfg::CH;
+      const int r = p / kHaloW, col = p - r * kHaloW;
+      pc_dst[i] = c * Cfg::A_PLANE + p * 16;
+      pc_rel[i] = (r * a.w + col) * CIN + c * 8;
+      pc_rc[i] = (idx < kHaloPix * Cfg::CH) ? ((r << 8) | col) : -1;
+    }
     uint32_t fill = 0;      // running (tile, source) counter
     uint32_t arrived = 0;   // fills already signalled on their full barrier
-    for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
-      const long long pt = tile / g.ntiles_n;
-      const int n = static_cast<int>(pt / tiles_per_img);
-      const int rem = static_cast<int>(pt % tiles_per_img);
-      const int y0 = (rem / g.tiles_x) * kTileH - 1;
-      const int x0 = (rem % g.tiles_x) * kTileW - 1;
+    for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+      const int pt = tile / g.ntiles_n;
+      const int n = pt / tiles_per_img;
+      const int rem = pt - n * tiles_per_img;
+      const int ty = rem / g.tiles_x;
+      const int y0 = ty * kTileH - 1;
+      const int x0 = (rem - ty * g.tiles_x) * kTileW - 1;
+      const long long origin = ((static_cast<long long>(n) * a.h + y0) * a.w + x0) * CIN;
       for (int s = 0; s < a.num_src; ++s, ++fill) {
         const int stage = fill % NSTAGE;
-        mbar_wait(empty_bar(stage), ((fill / NSTAGE) & 1) ^ 1);
-        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.src[s]);
+        if (ptid == 0) tl_stamp(g, 0, fill, 0);
+        mbar_wait_relaxed(empty_bar(stage), ((fill / NSTAGE) & 1) ^ 1);
+        if (ptid == 0) tl_stamp(g, 0, fill, 1);
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.src[s]) + origin;
         const uint32_t dst0 = smem_u32(sA + stage * Cfg::A_STAGE);
-#pragma unroll 4
-        for (int idx = ptid; idx < kHaloPix * Cfg::CH; idx += kProdThreads) {
-          const int p = idx / Cfg::CH, c = idx % Cfg::CH;
-          const int r = p / kHaloW, col = p % kHaloW;
-          const int gy = y0 + r, gx = x0 + col;
-          const bool inb = (gy >= 0) && (gy < a.h) && (gx >= 0) && (gx < a.w);
-          const size_t off = inb ? ((static_cast<size_t>(n) * a.h + gy) * a.w + gx) * CIN + c * 8 : 0;
-          cp_async16(dst0 + c * Cfg::A_PLANE + p * 16, src + off, inb ? 16u : 0u);
+#pragma unroll
+        for (int i = 0; i < Cfg::PROD_PIECES; ++i) {
+          if (pc_rc[i] >= 0) {
+            const int gy = y0 + (pc_rc[i] >> 8), gx = x0 + (pc_rc[i] & 0xff);
+            const bool inb = (static_cast<unsigned>(gy) < static_cast<unsigned>(a.h)) &&
+                             (static_cast<unsigned>(gx) < static_cast<unsigned>(a.w));
+            cp_async16(dst0 + pc_dst[i], inb ? (src + pc_rel[i]) : reinterpret_cast<const __nv_bfloat16*>(a.src[s]),
+                       inb ? 16u : 0u);
+          }
         }
         cp_async_commit();
+        if (ptid == 0) tl_stamp(g, 0, fill, 2);
         if (fill >= static_cast<uint32_t>(Cfg::LAG)) {
           cp_async_wait<Cfg::LAG>();
           fence_proxy_async_smem();
           mbar_arrive(full_bar(arrived % NSTAGE));
+          if (ptid == 0) tl_stamp(g, 0, arrived, 3);
           ++arrived;
         }
       }
     }
+    // drain oldest-first so a short tile list does not wait for its last load before the first MMA starts
+    if (Cfg::LAG == 2 && fill - arrived == 2) {
+      cp_async_wait<1>();
+      fence_proxy_async_smem();
+      mbar_arrive(full_bar(arrived % NSTAGE));
+      ++arrived;
+    }
     cp_async_wait<0>();
     fence_proxy_async_smem();
     for (; arrived < fill; ++arrived) mbar_arrive(full_bar(arrived % NSTAGE));
-  } else if (warp == 4) {
-    // =============================== MMA issuer (one elected thread) ==============================
-    if (lane == 0) {
+  } else if (warp == kMmaWarp) {
+    // =============================== MMA issuer (one elected lane) ================================
+    if (elect_one()) {  // elect.sync: lets the compiler prove single-lane execution (no per-MMA lane waterfall)
       // resident weights: one bulk copy per (src,tap) block
       mbar_arrive_expect_tx(wbar, w_bytes);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.weights) + static_cast<size_t>(ntile) * w_bytes;
@@ -131,16 +183,19 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, NT, 0, 0);
       const uint32_t sW_addr = smem_u32(sW);
       uint32_t fill = 0, k = 0;
-      for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++k) {
+      for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++k) {
         const uint32_t as = k & 1;
+        tl_stamp(g, 1, k, 0);
         mbar_wait(tempty_bar(as), ((k >> 1) & 1) ^ 1);
         tc_fence_after_sync();
+        tl_stamp(g, 1, k, 1);
         const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
         uint32_t accumulate = 0;
         for (int s = 0; s < a.num_src; ++s, ++fill) {
           const int stage = fill % NSTAGE;
           mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
           tc_fence_after_sync();
+          tl_stamp(g, 1, k, 2);
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_STAGE);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
@@ -157,40 +212,149 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
           umma_commit(empty_bar(stage));  // halo stage reusable once these MMAs retire
         }
         umma_commit(tfull_bar(as));       // accumulator ready for the epilogue
+        tl_stamp(g, 1, k, 3);
       }
     }
     __syncwarp();
   } else {
-    // =============================== epilogue: TMEM -> registers -> global ========================
-    const int m = threadIdx.x;            // TMEM lane == tile pixel index
+    // =============================== epilogue: TMEM -> registers -> (smem ->) global ==============
+    const int eg = warp >> 2, q = warp & 3;  // epilogue group == TMEM accumulator stage, TMEM lane quarter
+    const int m = q * 32 + lane;             // TMEM lane == tile pixel index == thread index within the group
     const int r = m >> 3, c = m & 7;
     float loss = 0.f;
-    uint32_t k = 0;
-    for (long long tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++k) {
-      const long long pt = tile / g.ntiles_n;
-      const int n = static_cast<int>(pt / tiles_per_img);
-      const int rem = static_cast<int>(pt % tiles_per_img);
-      const int y = (rem / g.tiles_x) * kTileH + r;
-      const int x = (rem % g.tiles_x) * kTileW + c;
+    const void* rp[kMaxRes] = {nullptr, nullptr, nullptr};
+    int ri_mask = -1, ri_res1 = -1, ri_res2 = -1, nr = 0;
+    if (a.mask != nullptr) { rp[nr] = a.mask; ri_mask = nr++; }
+    if (a.res1 != nullptr) { rp[nr] = a.res1; ri_res1 = nr++; }
+    if (a.res2 != nullptr) { rp[nr] = a.res2; ri_res2 = nr++; }
+    constexpr int kPitch = Cfg::PIX_PITCH;       // staged pixel pitch in bytes
+    constexpr int kPieces = 128 * NT / 8 / 128;  // 16 B pieces per thread per tile (= NT/8)
+    // tile-invariant description of this thread's pieces for the coalesced copy-out / residual prefetch:
+    // piece pc = m + 128*i  ->  pixel pc/(NT/8) of the tile, channel chunk pc%(NT/8)
+    uint32_t ep_smem[kPieces];
+    int ep_rel[kPieces], ep_rc[kPieces];
+#pragma unroll
+    for (int i = 0; i < kPieces; ++i) {
+      const int pc = m + 128 * i;
+      const int px = pc / (NT / 8), ch = pc - px * (NT / 8);
+      ep_smem[i] = px * kPitch + ch * 16;
+      ep_rel[i] = ((px >> 3) * a.w + (px & 7)) * NT + ch * 8;
+      ep_rc[i] = ((px >> 3) << 8) | (px & 7);
+    }
+    uint8_t* sOut = sEpi + eg * epi_bytes;
+    uint8_t* sRes = sOut + Cfg::OUT_TILE;
+    const bool tl0 = (threadIdx.x == 0);
+    const bool unit_scale = (a.res_scale == 1.0f);
+    const uint32_t as = eg;
+
+    auto decode = [&](int tile, int& n, int& ty0, int& tx0) {
+      const int pt = tile / g.ntiles_n;
+      n = pt / tiles_per_img;
+      const int rem = pt - n * tiles_per_img;
+      const int tyi = rem / g.tiles_x;
+      ty0 = tyi * kTileH;
+      tx0 = (rem - tyi * g.tiles_x) * kTileW;
+    };
+    // cp.async the mask/residual tiles of `tile` into this group's sRes (dense NHWC rows, 16 B pieces, coalesced)
+    auto prefetch_res = [&](int tile) {
+      if (tile < g.total_tiles) {
+        int n, ty0, tx0;
+        decode(tile, n, ty0, tx0);
+        const long long origin = ((static_cast<long long>(n) * a.h + ty0) * a.w + tx0) * NT;
+        const int vh = a.h - ty0, vw = a.w - tx0;
+        for (int i = 0; i < nr; ++i) {
+          const __nv_bfloat16* gsrc = reinterpret_cast<const __nv_bfloat16*>(rp[i]) + origin;
+          const uint32_t dst = smem_u32(sRes + i * Cfg::OUT_TILE);
+#pragma unroll
+          for (int j = 0; j < kPieces; ++j) {
+            if ((ep_rc[j] >> 8) < vh && (ep_rc[j] & 0xff) < vw) cp_async16(dst + ep_smem[j], gsrc + ep_rel[j], 16u);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+
+    const int tile_stride = 2 * gridDim.x;
+    uint32_t k = eg;                          // CTA-local tile counter (parity == accumulator stage)
+    int tile = blockIdx.x + eg * gridDim.x;
+    if (L.staged && nr > 0) prefetch_res(tile);
+
+    for (; tile < g.total_tiles; tile += tile_stride, k += 2) {
+      int n, ty0, tx0;
+      decode(tile, n, ty0, tx0);
+      const int y = ty0 + r, x = tx0 + c;
       const bool valid = (y < a.h) && (x < a.w);
-      const uint32_t as = k & 1;
-      mbar_wait(tfull_bar(as), (k >> 1) & 1);
+
+      if (tl0) tl_stamp(g, 2, k, 0);
+      mbar_wait_relaxed(tfull_bar(as), (k >> 1) & 1);
       tc_fence_after_sync();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + as * Cfg::ACC_STRIDE;
-      if constexpr (NT <= 64) {
-        // read the whole accumulator first so the TMEM stage is released before the global traffic
+      if (tl0) tl_stamp(g, 2, k, 1);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+
+      if (L.staged) {
         float v[NT];
 #pragma unroll
         for (int j = 0; j < NT / 16; ++j) tmem_ld16(taddr + j * 16, v + j * 16);
         tmem_ld_wait();
         tc_fence_before_sync();
-        mbar_arrive(tempty_bar(as));
-        if (valid) {
+        mbar_arrive(tempty_bar(as));      // accumulator stage free: this group's next tile may be accumulated
+        if (tl0) tl_stamp(g, 2, k, 2);
+        if (nr > 0) cp_async_wait<0>();   // my pieces of this tile's residual rows have landed
+        named_bar_sync(1 + eg, 128);      // A: all residual pieces visible; previous copy-out finished reading sOut
+        if (tl0) tl_stamp(g, 3, k, 0);
+        const __nv_bfloat16* myres = reinterpret_cast<const __nv_bfloat16*>(sRes + m * kPitch);
+        __nv_bfloat16* myout = reinterpret_cast<__nv_bfloat16*>(sOut + m * kPitch);
+        const float* bias = sBias + ntile * NT;
 #pragma unroll
-          for (int j = 0; j < NT / 16; ++j)
-            loss += conv_epilogue16<__nv_bfloat16>(a, n, y, x, ntile * NT + j * 16, v + j * 16);
+        for (int j = 0; j < NT / 8; ++j) {
+          float* vj = v + j * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vj[i] += bias[j * 8 + i];
+          if (!unit_scale) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vj[i] *= a.res_scale;
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vj[i] = fmaxf(vj[i], 0.f);
+          }
+          if (ri_mask >= 0) {
+            float t[8];
+            load8(myres + ri_mask * (Cfg::OUT_TILE / 2) + j * 8, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vj[i] = (t[i] > 0.f) ? vj[i] : 0.f;
+          }
+          if (ri_res1 >= 0) {
+            float t[8];
+            load8(myres + ri_res1 * (Cfg::OUT_TILE / 2) + j * 8, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vj[i] += t[i];
+          }
+          if (ri_res2 >= 0) {
+            float t[8];
+            load8(myres + ri_res2 * (Cfg::OUT_TILE / 2) + j * 8, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vj[i] += t[i];
+          }
+          store8(myout + j * 8, vj);
         }
+        named_bar_sync(3 + eg, 128);      // B: tile staged in sOut; everyone is done reading sRes
+        if (tl0) tl_stamp(g, 3, k, 2);
+        if (nr > 0) prefetch_res(tile + tile_stride);   // next tile of this group, hidden behind the other group's turn
+        // coalesced copy-out: consecutive threads write consecutive 16 B of a tile row
+        {
+          __nv_bfloat16* gout = reinterpret_cast<__nv_bfloat16*>(a.out) +
+                                ((static_cast<long long>(n) * a.h + ty0) * a.w + tx0) * NT;
+          const int vh = a.h - ty0, vw = a.w - tx0;
+#pragma unroll
+          for (int j = 0; j < kPieces; ++j) {
+            if ((ep_rc[j] >> 8) < vh && (ep_rc[j] & 0xff) < vw)
+              *reinterpret_cast<uint4*>(gout + ep_rel[j]) = *reinterpret_cast<const uint4*>(sOut + ep_smem[j]);
+          }
+        }
+        if (tl0) tl_stamp(g, 2, k, 3);
       } else {
+        // direct path (PixelShuffle / RGB / multi-N-tile epilogues)
 #pragma unroll 1
         for (int j = 0; j < NT / 16; ++j) {
           float v[16];
@@ -202,6 +366,7 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
         mbar_arrive(tempty_bar(as));
       }
     }
+    if (L.staged && nr > 0) cp_async_wait<0>();
     if (a.truth_hr != nullptr && a.loss_sum != nullptr) {
       loss = warp_sum(loss);
       if (lane == 0) atomicAdd(a.loss_sum, static_cast<double>(loss));
@@ -210,7 +375,7 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after_sync();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
@@ -225,10 +390,13 @@ int pick_ntile(int cout_pad) {
   return nt;
 }
 
+long long* g_timeline = nullptr;
+constexpr size_t kMaxSmem = 227 * 1024;
+
 template <int CIN, int NT, int NSTAGE>
-static int launch_tc(const lv_conv_args& a, const ConvGeom& g, int max_ctas, cudaStream_t stream) {
+static int launch_tc(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L, int max_ctas, cudaStream_t stream) {
   using Cfg = TcCfg<CIN, NT, NSTAGE>;
-  const size_t smem = Cfg::smem_bytes(a.num_src);
+  const size_t smem = Cfg::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad);
   auto kern = conv3x3_tc_kernel<CIN, NT, NSTAGE>;
   static size_t configured = 0;
   if (smem > configured) {
@@ -239,32 +407,47 @@ static int launch_tc(const lv_conv_args& a, const ConvGeom& g, int max_ctas, cud
   if (ctas > g.total_tiles) ctas = g.total_tiles;
   ctas = (ctas / g.ntiles_n) * g.ntiles_n;
   if (ctas < g.ntiles_n) ctas = g.ntiles_n;
-  kern<<<static_cast<unsigned>(ctas), kTcThreads, smem, stream>>>(a, g);
+  kern<<<static_cast<unsigned>(ctas), kTcThreads, smem, stream>>>(a, g, L);
   LV_LAUNCH_OK();
   return LV_OK;
 }
 
+// pick the deepest halo pipeline that fits in shared memory
+template <int CIN, int NT>
+static int dispatch_stages(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L, int max_ctas, cudaStream_t stream) {
+  if (TcCfg<CIN, NT, 4>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
+    return launch_tc<CIN, NT, 4>(a, g, L, max_ctas, stream);
+  if (TcCfg<CIN, NT, 3>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
+    return launch_tc<CIN, NT, 3>(a, g, L, max_ctas, stream);
+  if (TcCfg<CIN, NT, 2>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
+    return launch_tc<CIN, NT, 2>(a, g, L, max_ctas, stream);
+  set_error("conv3x3 tensor-core path: cin=%d x %d sources, cout tile %d does not fit in shared memory", CIN, a.num_src, NT);
+  return LV_ERR_INVALID;
+}
+
 int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream) {
   ConvGeom g;
+  g.timeline = g_timeline;
   g.cout_pad = (a.cout + 15) / 16 * 16;
   g.nt = pick_ntile(g.cout_pad);
   g.ntiles_n = g.cout_pad / g.nt;
   g.tiles_x = (a.w + kTileW - 1) / kTileW;
   g.tiles_y = (a.h + kTileH - 1) / kTileH;
-  g.total_tiles = static_cast<long long>(a.n) * g.tiles_x * g.tiles_y * g.ntiles_n;
-  if (g.total_tiles == 0) return LV_OK;
-#define LV_TC_CASE(CI, NTV, NS) \
-  if (a.cin == CI && g.nt == NTV) return launch_tc<CI, NTV, NS>(a, g, max_ctas, stream);
-  if (a.num_src <= 2) {
-    LV_TC_CASE(48, 48, 4)
-  } else {
-    LV_TC_CASE(48, 48, 3)
-  }
-  LV_TC_CASE(48, 96, 3)
-  LV_TC_CASE(64, 64, 3)
-  LV_TC_CASE(64, 128, 3)
-  LV_TC_CASE(64, 16, 3)
-  LV_TC_CASE(48, 16, 3)
+  const long long tt = static_cast<long long>(a.n) * g.tiles_x * g.tiles_y * g.ntiles_n;
+  if (tt == 0) return LV_OK;
+  LV_CHECK_ARG(tt < (1ll << 31), "conv3x3: too many tiles (%lld)", tt);
+  g.total_tiles = static_cast<int>(tt);
+  TcLaunch L;
+  L.staged = (a.epilogue == LV_EPI_NHWC && g.ntiles_n == 1 && a.cout == g.cout_pad) ? 1 : 0;
+  L.nres = (a.mask != nullptr) + (a.res1 != nullptr) + (a.res2 != nullptr);
+#define LV_TC_CASE(CI, NTV) \
+  if (a.cin == CI && g.nt == NTV) return dispatch_stages<CI, NTV>(a, g, L, max_ctas, stream);
+  LV_TC_CASE(48, 48)
+  LV_TC_CASE(48, 96)
+  LV_TC_CASE(64, 64)
+  LV_TC_CASE(64, 128)
+  LV_TC_CASE(64, 16)
+  LV_TC_CASE(48, 16)
 #undef LV_TC_CASE
   set_error("conv3x3 tensor-core path: unsupported shape cin=%d cout=%d (n-tile %d)", a.cin, a.cout, g.nt);
   return LV_ERR_INVALID;

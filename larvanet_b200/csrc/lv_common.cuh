@@ -99,6 +99,19 @@ __device__ __forceinline__ void store16(__nv_bfloat16* p, const float* v) {
   }
 }
 
+// 8 consecutive bf16 channels (16 B)
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float* v) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  v[0] = bf16_lo(t.x); v[1] = bf16_hi(t.x); v[2] = bf16_lo(t.y); v[3] = bf16_hi(t.y);
+  v[4] = bf16_lo(t.z); v[5] = bf16_hi(t.z); v[6] = bf16_lo(t.w); v[7] = bf16_hi(t.w);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) {
+  uint4 t;
+  t.x = pack_bf16x2(v[0], v[1]); t.y = pack_bf16x2(v[2], v[3]);
+  t.z = pack_bf16x2(v[4], v[5]); t.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -157,6 +170,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
   }
 }
+// Relaxed wait for roles that are normally far ahead of the barrier (producers on `empty`, epilogue on `tmem_full`):
+// the suspend-time hint lets the hardware park the thread instead of re-issuing try_wait, so spinning warps do not eat
+// the issue slots of the warps that are doing the work (measured: ~35 % of all issued instructions were spin loops).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity, 400u)) {
+    if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+  }
+}
 
 // ---- proxy / tcgen05 fences ----
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -183,6 +216,23 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// ---- TMA bulk copy shared -> global (1-D), bulk-group completion ----
+__device__ __forceinline__ void tma_bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until the sources of all but the N most recent bulk groups have been read (smem reusable)
+template <int N> __device__ __forceinline__ void tma_bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N> __device__ __forceinline__ void tma_bulk_wait() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// named barrier among a subset of the CTA's warps (id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 // ---- TMEM allocation (one full warp executes these) ----
@@ -242,6 +292,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
         "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
       : "r"(taddr)
       : "memory");
+}
+// TMEM -> registers: this warp's 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

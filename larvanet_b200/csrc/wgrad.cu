@@ -106,7 +106,7 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
     for (; arrived < fill; ++arrived) mbar_arrive(full_bar(arrived % kWStages));
   } else if (warp == 4) {
     // ------------------------------- MMA issuer -------------------------------
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc_w = umma_idesc_bf16(64, kWCin, 1, 1);
       constexpr uint32_t idesc_b = umma_idesc_bf16(64, 8, 1, 1);
       const uint32_t ones_addr = smem_u32(sOnes);

@@ -409,7 +409,28 @@ class LarvaEngine:
         denom = self.m + 1 if self.v2 else self.m
         numel = n * 3 * 16 * h * w * self.world_size
         self.last_exits = b.exits
+        self._last_train = b
         return b.loss_sum[0] / (float(numel) * denom)
+
+    def saved_activations(self):
+        """The forward activations the last train_step saved for its backward pass, as NCHW float32 CPU tensors keyed
+        like oracle.larva_oracle.larvanet_train_step(tapes_from=...).  For parity tests / debugging only."""
+        b = self._last_train
+
+        def cv(a):
+            return a.detach().to(torch.float32).permute(0, 3, 1, 2).contiguous().cpu().numpy()
+
+        t = {'f0': cv(b.f0)}
+        for i, nb in enumerate(self.blocks):
+            t[('feat', i)] = cv(b.feats[i])
+            t[('u', i)] = cv(b.u[i])
+            for j in range(nb):
+                t[('t', i, j)] = cv(b.t[i][j])
+                if j > 0:
+                    t[('a', i, j)] = cv(b.a[i][j - 1])
+        if self.v2:
+            t['mf'], t['ut'] = cv(b.mf), cv(b.ut)
+        return t
 
     # ------------------------------------------------------------------ individually-callable modules
     # The reference's train step and analysis scripts call sub-modules one by one with NCHW fp32 tensors

@@ -251,16 +251,21 @@ def larvanet_v2_forward(params, x, blocks, dtype=np.float64):
     return out
 
 
-def larvanet_train_step(params, x, truth, blocks, v2=False, dtype=np.float64, sign_from=None):
+def larvanet_train_step(params, x, truth, blocks, v2=False, dtype=np.float64, sign_from=None, tapes_from=None):
     """Forward + backward core of train_step_larva.
 
     V1: reference models/LarvaNet.py:102-113 -- loss = sum_i L1(leg_i(body_i(..)), truth) / M.
     V2: reference models/LarvaNetV2.py:105-118 -- M leg losses + tail loss, divided by M+1.
     Returns (loss, grads dict keyed like state_dict, list of per-exit outputs).
 
-    `sign_from` (optional list of per-exit output arrays) replaces the oracle's own exit outputs inside
-    sign(out - truth) only.  The L1 gradient is discontinuous, so a parity test of the BACKWARD kernels feeds the
-    device's exit outputs here; the pure-oracle gradient (sign_from=None) is what is pinned to the reference.
+    Two optional hooks exist for parity tests of a reduced-precision device path, because ReLU and the L1 sign are
+    discontinuous (a forward error of 1e-2 flips a few masks/signs, which moves gradients by several percent in L2
+    although every kernel is exact):
+      `sign_from`  : list of per-exit output arrays used inside sign(out - truth) instead of the oracle's own exits;
+      `tapes_from` : dict of the device's saved forward activations (NCHW): 'f0', ('a',i,j) block inputs for j>0,
+                     ('t',i,j) post-ReLU, ('feat',i), ('u',i) and for V2 'mf','ut'.  The backward pass then runs on
+                     exactly the state the device's backward kernels saw.
+    With both None this is the plain oracle that is pinned to the reference's golden outputs.
     """
     x = np.asarray(x, dtype)
     truth = np.asarray(truth, dtype)
@@ -279,6 +284,7 @@ def larvanet_train_step(params, x, truth, blocks, v2=False, dtype=np.float64, si
         leg_tapes.append(ltp)
         outs.append(out)
         loss += l1_loss(out, truth)
+    cat = mw = ttp = None
     if v2:
         cat = np.concatenate(feats, axis=1)
         mw = _p(params, 'tail.merge_conv.weight', dtype)
@@ -288,17 +294,28 @@ def larvanet_train_step(params, x, truth, blocks, v2=False, dtype=np.float64, si
         loss += l1_loss(tout, truth)
     loss = loss / denom
 
+    if tapes_from is not None:
+        T = {k: np.asarray(v, dtype) for k, v in tapes_from.items()}
+        feats = [T[('feat', i)] for i in range(m)]
+        body_tapes = []
+        for i in range(m):
+            fin = T['f0'] if i == 0 else feats[i - 1]
+            body_tapes.append([(fin if j == 0 else T[('a', i, j)], T[('t', i, j)]) for j in range(blocks[i])])
+        leg_tapes = [(feats[i], T[('u', i)]) for i in range(m)]
+        if v2:
+            cat = np.concatenate(feats, axis=1)
+            ttp = (T['mf'], T['ut'])
+    souts = outs if sign_from is None else [np.asarray(o, dtype) for o in sign_from]
+
     grads = {}
     dfeats = [np.zeros_like(f) for f in feats]
     if v2:
-        souts = outs if sign_from is None else [np.asarray(o, dtype) for o in sign_from]
         dmfea = _recon_bwd(params, 'tail', ttp, l1_loss_grad(souts[m], truth, 1.0 / denom), grads, dtype)
         dcat, dmw, dmb = conv2d_backward(cat, mw, dmfea)
         grads['tail.merge_conv.weight'] = dmw
         grads['tail.merge_conv.bias'] = dmb
         for i in range(m):
             dfeats[i] = dfeats[i] + dcat[:, NUM_FILTERS * i:NUM_FILTERS * (i + 1)]
-    souts = outs if sign_from is None else [np.asarray(o, dtype) for o in sign_from]
     dnext = None
     for i in reversed(range(m)):
         d = dfeats[i] + _recon_bwd(params, f'body_{i}.leg', leg_tapes[i],

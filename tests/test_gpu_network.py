@@ -76,20 +76,22 @@ def test_train_step_loss_and_grads(golden_dir, name, precision):
     for k, e in enumerate(eng.last_exits):
         err = np.max(np.abs(e.cpu().numpy() - ref_outs[k]))
         assert err <= (1e-4 * 255 if precision == 'fp32' else 2.0)
-    # The L1 gradient sign(out - truth) is discontinuous: where |out - truth| is below the forward error the sign
-    # flips, and a fraction f of flipped signs alone moves the gradient by 2*sqrt(f) in relative L2.  The backward
-    # kernels are therefore checked against the oracle's backward driven by the DEVICE's exit outputs (same signs),
-    # and the end-to-end gradient against the pure oracle with the flip budget added.
+    # ReLU masks and the L1 sign are discontinuous: a forward error of ~1e-2 (bf16 activations) flips a fraction f of
+    # them, and that alone moves a gradient by ~2*sqrt(f) in relative L2 (measured 2.5-5 % here) although every
+    # kernel is exact.  So (a) the BACKWARD KERNELS are checked against the oracle's backward evaluated on the
+    # device's own saved forward state (same masks, same signs, same wgrad inputs), tight tolerance; (b) the
+    # end-to-end gradient is checked against the pure oracle (pinned to the reference) with the discontinuity budget.
     dev_exits = [e.cpu().numpy() for e in eng.last_exits]
-    _, same_sign_grads, _ = O.larvanet_train_step(params, lr, hr, blocks, v2=v2, sign_from=dev_exits)
-    flips = np.mean([np.mean(np.sign(d - hr) != np.sign(r - hr)) for d, r in zip(dev_exits, ref_outs)])
+    _, same_state_grads, _ = O.larvanet_train_step(params, lr, hr, blocks, v2=v2, sign_from=dev_exits,
+                                                   tapes_from=eng.saved_activations())
+    e2e_tol = 1e-3 if precision == 'fp32' else 8e-2
     for name_, p in m.get_model().named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape
         got = p.grad.cpu().numpy()
-        r = rel_l2(got, same_sign_grads[name_])
+        r = rel_l2(got, same_state_grads[name_])
         assert r <= gtol, (name_, r)
         r2 = rel_l2(got, ref_grads[name_])
-        assert r2 <= gtol + 4.0 * np.sqrt(flips), (name_, r2, flips)
+        assert r2 <= e2e_tol, (name_, r2)
     if precision == 'bf16':
         # replay (CUDA graph) reproduces the same conv gradients bit for bit (deterministic split-K reduction);
         # the head gradient uses fp32 atomics and is excluded, as is the fp32 validation mode (atomics throughout)
