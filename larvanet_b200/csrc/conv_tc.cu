@@ -123,7 +123,6 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
       pc_rc[i] = (idx < kHaloPix * Cfg::CH) ? ((r << 8) | col) : -1;
     }
     uint32_t fill = 0;      // running (tile, source) counter
-    uint32_t arrived = 0;   // fills already signalled on their full barrier
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
       const int pt = tile / g.ntiles_n;
       const int n = pt / tiles_per_img;
@@ -149,27 +148,13 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
                        inb ? 16u : 0u);
           }
         }
-        cp_async_commit();
+        // asynchronous arrival: the full barrier completes when every producer thread's copies of this fill have
+        // landed (same producer->UMMA hand-off as CUTLASS' sm100 cp.async mainloop); the producer never blocks on loads
+        cp_async_mbar_arrive_noinc(full_bar(stage));
         if (ptid == 0) tl_stamp(g, 0, fill, 2);
-        if (fill >= static_cast<uint32_t>(Cfg::LAG)) {
-          cp_async_wait<Cfg::LAG>();
-          fence_proxy_async_smem();
-          mbar_arrive(full_bar(arrived % NSTAGE));
-          if (ptid == 0) tl_stamp(g, 0, arrived, 3);
-          ++arrived;
-        }
       }
     }
-    // drain oldest-first so a short tile list does not wait for its last load before the first MMA starts
-    if (Cfg::LAG == 2 && fill - arrived == 2) {
-      cp_async_wait<1>();
-      fence_proxy_async_smem();
-      mbar_arrive(full_bar(arrived % NSTAGE));
-      ++arrived;
-    }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (; arrived < fill; ++arrived) mbar_arrive(full_bar(arrived % NSTAGE));
+    cp_async_wait<0>();   // nothing of ours may still be in flight when the CTA retires
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer (one elected lane) ================================
     if (elect_one()) {  // elect.sync: lets the compiler prove single-lane execution (no per-MMA lane waterfall)
@@ -194,6 +179,7 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
         for (int s = 0; s < a.num_src; ++s, ++fill) {
           const int stage = fill % NSTAGE;
           mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
+          fence_proxy_async_smem();   // consumer-side: cp.async (generic proxy) writes -> UMMA (async proxy) reads
           tc_fence_after_sync();
           tl_stamp(g, 1, k, 2);
           const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_STAGE);

@@ -1,0 +1,57 @@
+"""Data-parallel plumbing for the training path (one process per GPU, torch.distributed over NCCL/NVLink).
+
+The reference is single-process; batch-sharded training is a new capability whose contract is:
+the result of G ranks, each holding B/G patches, must equal the reference's single-process step on the global batch B.
+With a mean-reduced L1 loss that means every rank scales its local gradient SUM by 1/(numel_global * exits) -- done
+inside the weight-gradient kernels via `grad_scale()` -- and the exchange is a plain SUM all-reduce of the flat gradient
+arena (3.3 MB fp32 for LarvaNet M=4: latency-bound, one bucket) plus the 8-byte loss sum.  Inference shards frames
+round-robin and needs no collective.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard_range(total, rank, world):
+    """[begin, end) of the contiguous shard of `total` items owned by `rank` (first `total % world` ranks get one more)."""
+    base, extra = divmod(total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def grad_scale(local_hr_numel, world, num_exits):
+    """Scale applied to a rank's local sum of sign(out - truth) so that the all-reduced SUM equals the gradient of the
+    reference's mean-reduced multi-exit loss over the global batch (reference models/LarvaNet.py:104-109)."""
+    return 1.0 / (float(local_hr_numel) * world * num_exits)
+
+
+def allreduce_gradients(flat_grad, loss_sum=None, group=None):
+    """SUM all-reduce of the flat gradient arena (and the loss accumulator).  Returns the async work handles."""
+    works = [dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group, async_op=True)]
+    if loss_sum is not None:
+        works.append(dist.all_reduce(loss_sum, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    return works
+
+
+def frames_for_rank(num_frames, rank, world):
+    """Round-robin frame indices for batch-sharded inference (no collective)."""
+    return list(range(rank, num_frames, world))

@@ -403,9 +403,9 @@ class LarvaEngine:
         else:
             self._run_train(b)
         if self.world_size > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.arena.grad, group=self.process_group)
-            dist.all_reduce(b.loss_sum, group=self.process_group)
+            from . import dist as lvdist
+            for work in lvdist.allreduce_gradients(self.arena.grad, b.loss_sum, self.process_group):
+                work.wait()   # stream-ordered on NCCL: enqueues a wait on the current stream, no host sync
         denom = self.m + 1 if self.v2 else self.m
         numel = n * 3 * 16 * h * w * self.world_size
         self.last_exits = b.exits

@@ -84,7 +84,7 @@ def test_train_step_loss_and_grads(golden_dir, name, precision):
     dev_exits = [e.cpu().numpy() for e in eng.last_exits]
     _, same_state_grads, _ = O.larvanet_train_step(params, lr, hr, blocks, v2=v2, sign_from=dev_exits,
                                                    tapes_from=eng.saved_activations())
-    e2e_tol = 1e-3 if precision == 'fp32' else 8e-2
+    e2e_tol = 1e-3 if precision == 'fp32' else 0.15   # discontinuity budget (mask/sign flips), see above
     for name_, p in m.get_model().named_parameters():
         assert p.grad is not None and p.grad.shape == p.shape
         got = p.grad.cpu().numpy()
@@ -92,6 +92,9 @@ def test_train_step_loss_and_grads(golden_dir, name, precision):
         assert r <= gtol, (name_, r)
         r2 = rel_l2(got, ref_grads[name_])
         assert r2 <= e2e_tol, (name_, r2)
+        cos = float(np.sum(got.astype(np.float64) * ref_grads[name_]) /
+                    (np.linalg.norm(got.astype(np.float64)) * np.linalg.norm(ref_grads[name_]) + 1e-300))
+        assert cos >= 0.985, (name_, cos)
     if precision == 'bf16':
         # replay (CUDA graph) reproduces the same conv gradients bit for bit (deterministic split-K reduction);
         # the head gradient uses fp32 atomics and is excluded, as is the fp32 validation mode (atomics throughout)

@@ -1,0 +1,141 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header declares, the plugin
+surface mirrors the reference's (flags, state_dict layout, error behaviour), and computing without a GPU fails loudly."""
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from larvanet_b200 import _lib, synth
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(REPO, 'include', 'larvanet_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(lv_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations found'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()   # binds every symbol or raises
+    assert lib.lv_abi_version() == _lib.ABI_VERSION
+    assert lib.lv_packed_weight_bytes(48, 48, _lib.LV_BF16) == 48 * 48 * 9 * 2
+    assert lib.lv_packed_weight_bytes(3, 64, _lib.LV_F32) == 16 * 64 * 9 * 4
+    assert lib.lv_launch_count() == 0
+
+
+def test_ctypes_struct_layout_matches_header_sizes():
+    import ctypes as C
+    # 12 x 4-byte scalars, then 17 pointers (4 sources + 13 others)
+    assert C.sizeof(_lib.ConvArgs) == 12 * 4 + 17 * 8
+    assert C.sizeof(_lib.WgradItem) == 8 * 4 + 4 * 8 + 8
+    assert C.sizeof(_lib.PackItem) == 2 * 8 + 8 * 4
+
+
+@pytest.mark.parametrize('modname,v2', [('LarvaNet', False), ('larvanet', False), ('LarvaNetV2', True), ('larvanetv2', True)])
+def test_plugin_surface(modname, v2):
+    mod = importlib.import_module('models.' + modname)
+    m = mod.create_model()
+    args, rest = m.parse_args(['--num_modules=3', '--num_blocks=2,1,1', '--lr=1e-3', '--unknown_flag=7'])
+    assert rest == ['--unknown_flag=7'] and args.num_modules == 3 and args.lr == 1e-3
+    with pytest.raises(ValueError):
+        m.prepare(is_training=False, scales=[5])
+    with pytest.raises(ValueError):
+        m.prepare(is_training=False, scales=[2, 4])
+    m.prepare(is_training=True, scales=[4], global_step=7)
+    assert m.global_step == 7 and m.get_next_train_scale() == 4 and abs(m.get_lr() - 1e-3) < 1e-12
+    sd = m.get_model().state_dict()
+    shapes = synth.larva_param_shapes([2, 1, 1], v2=v2)
+    assert list(sd.keys()) == list(shapes.keys())
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+    # reference init statistics: kaiming-normal(fan_in) * 0.1, zero bias (models/LarvaNet.py:22-39)
+    w = sd['body_0.res_blocks.0.body.0.weight'].numpy()
+    assert abs(w.std() - 0.1 * np.sqrt(2.0 / 432)) < 0.1 * 0.1 * np.sqrt(2.0 / 432)
+    assert float(sd['body_0.res_blocks.0.body.0.bias'].abs().max()) == 0.0
+    for name in ('parse_args', 'prepare', 'save', 'restore', 'get_model', 'get_next_train_scale', 'train_step_larva',
+                 'validate_for_train', 'upscale', 'test', 'fwd_runtime', 'get_lr'):
+        assert callable(getattr(m, name))
+    mod2 = mod.create_model()
+    mod2.parse_args(['--num_modules=2', '--num_blocks=1,1,1'])
+    with pytest.raises(GeneratorExit):
+        mod2.prepare(is_training=False, scales=[4])
+
+
+def test_checkpoint_round_trip_and_v1_to_v2_warm_start(tmp_path):
+    v1 = importlib.import_module('models.LarvaNet').create_model()
+    v1.parse_args(['--num_modules=2', '--num_blocks=1,1'])
+    v1.prepare(is_training=False, scales=[4])
+    v1.total_volume = 3e9
+    v1.global_step = 12
+    v1.save(str(tmp_path))
+    ckpt = os.path.join(str(tmp_path), 'model_step12_vol3G.pth')
+    assert os.path.exists(ckpt) and os.path.getsize(ckpt) < 2 * sum(p.numel() * 4 for p in v1.get_model().parameters())
+    again = importlib.import_module('models.LarvaNet').create_model()
+    again.parse_args(['--num_modules=2', '--num_blocks=1,1'])
+    again.prepare(is_training=False, scales=[4])
+    again.restore(ckpt)
+    for k, v in v1.get_model().state_dict().items():
+        assert torch.equal(v, again.get_model().state_dict()[k])
+    v2 = importlib.import_module('models.LarvaNetV2').create_model()
+    v2.parse_args(['--num_modules=2', '--num_blocks=1,1'])
+    v2.prepare(is_training=False, scales=[4])
+    tail_before = v2.get_model().state_dict()['tail.merge_conv.weight'].clone()
+    v2.restore(ckpt)   # reference models/LarvaNetV2.py:196-206: keys the model lacks are ignored
+    sd2 = v2.get_model().state_dict()
+    assert torch.equal(sd2['head.feature_extraction.weight'], v1.get_model().state_dict()['head.feature_extraction.weight'])
+    assert torch.equal(sd2['tail.merge_conv.weight'], tail_before)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_compute_without_gpu_fails_loudly():
+    m = importlib.import_module('models.LarvaNet').create_model()
+    m.parse_args(['--num_modules=1', '--num_blocks=1'])
+    m.prepare(is_training=False, scales=[4])
+    with pytest.raises(_lib.LarvaNetB200Error):
+        m.upscale([np.zeros((3, 8, 8), np.float32)], 4)
+    with pytest.raises(_lib.LarvaNetB200Error):
+        m.get_model().head(torch.zeros(1, 3, 8, 8))
+    from larvanet_b200 import ops
+    with pytest.raises(_lib.LarvaNetB200Error):
+        ops.bicubic_x4(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 16, 16))
+
+
+def test_synthetic_loader_contract():
+    ld = importlib.import_module('dataloaders.synthetic_loader').create_loader()
+    _, rest = ld.parse_args(['--synthetic_images=2', '--synthetic_height=40', '--synthetic_width=56', '--x=1'])
+    assert rest == ['--x=1']
+    ld.prepare(scales=[4])
+    assert ld.get_num_images() == 2 and ld.is_threaded is False
+    inp, tru = ld.get_patch_batch(batch_size=3, scale=4, input_patch_size=16)
+    assert len(inp) == 3 and inp[0].shape == (3, 16, 16) and tru[0].shape == (3, 64, 64)
+    lr, hr, name = ld.get_image_pair(image_index=1, scale=4)
+    assert lr.shape == (3, 40, 56) and hr.shape == (3, 160, 224) and isinstance(name, str)
+    assert 0 <= lr.min() and hr.max() <= 255
+
+
+def test_psnr_helpers_match_oracle():
+    import validate
+    from oracle import larva_oracle as O
+    rs = np.random.RandomState(0)
+    a = rs.uniform(-5, 260, (3, 9, 7))
+    b = rs.uniform(0, 255, (3, 12, 9))
+    u8 = validate._image_to_uint8(a)
+    np.testing.assert_array_equal(u8, O.image_to_uint8(a))
+    t = validate._fit_truth_image_size(output_image=u8, truth_image=validate._image_to_uint8(b))
+    assert t.shape == u8.shape
+    assert abs(validate._image_psnr(u8, t) - O.image_psnr(u8, t)) < 1e-9
+
+
+def test_chop_forward_split_and_combine_are_inverse_for_identity_model():
+    from utils import image_utils
+
+    class Nearest:
+        def upscale(self, input_list, scale):
+            x = np.asarray(input_list)
+            return np.repeat(np.repeat(x, scale, axis=2), scale, axis=3)
+
+    img = np.random.RandomState(1).uniform(0, 255, (3, 22, 30))
+    out = image_utils.upscale_with_chop_forward(Nearest(), img, scale=4, overlap_size=10)
+    np.testing.assert_array_equal(out, np.repeat(np.repeat(img, 4, axis=1), 4, axis=2))
