@@ -71,39 +71,56 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
     const int ptid = threadIdx.x - 160;
     const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(it.x);
     const __nv_bfloat16* DY = reinterpret_cast<const __nv_bfloat16*>(it.dy);
-    uint32_t fill = 0, arrived = 0;
-    for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
-      const int n = tile / tiles_per_img, rem = tile % tiles_per_img;
-      const int y0 = (rem / tiles_x) * kWT_H, x0 = (rem % tiles_x) * kWT_W;
-      const int stage = fill % kWStages;
-      mbar_wait(empty_bar(stage), ((fill / kWStages) & 1) ^ 1);
-      const uint32_t dy0 = smem_u32(smem + stage * kWStageBytes);
-      const uint32_t xs0 = dy0 + kDyBytes;
-      for (int idx = ptid; idx < 128 * cho; idx += 128) {
-        const int p = idx / cho, c = idx % cho;
-        const int gy = y0 + (p >> 3), gx = x0 + (p & 7);
-        const bool inb = gy < it.h && gx < it.w;
-        const size_t off = inb ? ((static_cast<size_t>(n) * it.h + gy) * it.w + gx) * it.cout + c * 8 : 0;
-        cp_async16(dy0 + c * kDyPlane + p * 16, DY + off, inb ? 16u : 0u);
-      }
-      for (int idx = ptid; idx < kWHaloPix * (kWCin / 8); idx += 128) {
-        const int p = idx / (kWCin / 8), c = idx % (kWCin / 8);
-        const int gy = y0 - 1 + p / kWHaloW, gx = x0 - 1 + p % kWHaloW;
-        const bool inb = gy >= 0 && gy < it.h && gx >= 0 && gx < it.w;
-        const size_t off = inb ? ((static_cast<size_t>(n) * it.h + gy) * it.w + gx) * kWCin + c * 8 : 0;
-        cp_async16(xs0 + c * kXPlane + p * 16, X + off, inb ? 16u : 0u);
-      }
-      cp_async_commit();
-      if (fill >= 2) {
-        cp_async_wait<2>();
-        fence_proxy_async_smem();
-        mbar_arrive(full_bar(arrived % kWStages));
-        ++arrived;
+    // tile-invariant piece tables: dY tile pieces first (128 px x cout/8 chunks), then X halo pieces (180 px x 6)
+    constexpr int kMaxPieces = (128 * 8 + kWHaloPix * (kWCin / 8) + 127) / 128;  // 17 for cout = 64
+    uint32_t pc_dst[kMaxPieces];
+    int pc_rel[kMaxPieces], pc_rc[kMaxPieces];
+    const int n_dy = 128 * cho, n_all = n_dy + kWHaloPix * (kWCin / 8);
+#pragma unroll
+    for (int i = 0; i < kMaxPieces; ++i) {
+      const int idx = ptid + i * 128;
+      if (idx < n_dy) {
+        const int p = idx / cho, c = idx - p * cho;
+        pc_dst[i] = c * kDyPlane + p * 16;
+        pc_rel[i] = ((p >> 3) * it.w + (p & 7)) * it.cout + c * 8;
+        pc_rc[i] = ((p >> 3) << 8) | (p & 7);                       // bit 30 clear: dY piece (tile coordinates)
+      } else if (idx < n_all) {
+        const int j = idx - n_dy;
+        const int p = j / (kWCin / 8), c = j - p * (kWCin / 8);
+        const int r = p / kWHaloW, col = p - r * kWHaloW;
+        pc_dst[i] = kDyBytes + c * kXPlane + p * 16;
+        pc_rel[i] = ((r - 1) * it.w + (col - 1)) * kWCin + c * 8;
+        pc_rc[i] = (1 << 30) | (r << 8) | col;                      // bit 30 set: X halo piece (halo coordinates)
+      } else {
+        pc_dst[i] = 0; pc_rel[i] = 0; pc_rc[i] = -1;
       }
     }
+    uint32_t fill = 0;
+    for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
+      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+      const int ty = rem / tiles_x;
+      const int y0 = ty * kWT_H, x0 = (rem - ty * tiles_x) * kWT_W;
+      const int stage = fill % kWStages;
+      mbar_wait_relaxed(empty_bar(stage), ((fill / kWStages) & 1) ^ 1);
+      const uint32_t st0 = smem_u32(smem + stage * kWStageBytes);
+      const long long org = (static_cast<long long>(n) * it.h + y0) * it.w + x0;
+      const __nv_bfloat16* dy_org = DY + org * it.cout;
+      const __nv_bfloat16* x_org = X + org * kWCin;
+#pragma unroll
+      for (int i = 0; i < kMaxPieces; ++i) {
+        if (pc_rc[i] >= 0) {
+          const bool isx = (pc_rc[i] >> 30) != 0;
+          const int rr = (pc_rc[i] >> 8) & 0xff, cc = pc_rc[i] & 0xff;
+          const int gy = y0 + rr - (isx ? 1 : 0), gx = x0 + cc - (isx ? 1 : 0);
+          const bool inb = (static_cast<unsigned>(gy) < static_cast<unsigned>(it.h)) &&
+                           (static_cast<unsigned>(gx) < static_cast<unsigned>(it.w));
+          const __nv_bfloat16* src = isx ? x_org : dy_org;
+          cp_async16(st0 + pc_dst[i], inb ? (src + pc_rel[i]) : X, inb ? 16u : 0u);
+        }
+      }
+      cp_async_mbar_arrive_noinc(full_bar(stage));
+    }
     cp_async_wait<0>();
-    fence_proxy_async_smem();
-    for (; arrived < fill; ++arrived) mbar_arrive(full_bar(arrived % kWStages));
   } else if (warp == 4) {
     // ------------------------------- MMA issuer -------------------------------
     if (elect_one()) {
@@ -114,6 +131,7 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
       for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
         const int stage = fill % kWStages;
         mbar_wait(full_bar(stage), (fill / kWStages) & 1);
+        fence_proxy_async_smem();   // consumer-side: cp.async (generic proxy) writes -> UMMA (async proxy) reads
         tc_fence_after_sync();
         const uint32_t dy0 = smem_u32(smem + stage * kWStageBytes);
         const uint32_t xs0 = dy0 + kDyBytes;
@@ -137,7 +155,7 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
     __syncwarp();
   } else {
     // ------------------------------- epilogue: TMEM -> workspace -------------------------------
-    mbar_wait(done_bar, 0);
+    mbar_wait_relaxed(done_bar, 0);
     tc_fence_after_sync();
     // M = 64 accumulator layout: row r lives in TMEM lane 32*(r/16) + r%16
     const int co = warp * 16 + lane;

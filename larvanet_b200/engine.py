@@ -301,8 +301,11 @@ class LarvaEngine:
 
     def _make_wgrad(self, items, tiles, splits):
         if splits <= 0:
-            # ~2 CTAs worth of layers per SM in total, at least 1 and at most one split per tile
-            splits = max(1, min(tiles, (2 * self.sm_count + len(items) - 1) // len(items)))
+            # the wgrad CTA owns the whole TMEM (1 CTA/SM): fill whole waves of SMs, at most one split per tile and
+            # at least ~8 tiles per split so the TMEM drain + reduction stay small next to the MMAs
+            per_wave = max(1, self.sm_count // len(items))
+            waves = max(1, min(4, tiles // (8 * per_wave)))
+            splits = max(1, min(tiles, per_wave * waves))
         return ops.WgradBatch(items, splits, self.device)
 
     def set_data_parallel(self, world_size, process_group=None):
