@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "lv_common.cuh"
 
@@ -37,6 +38,7 @@ int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
 int conv3x3_simt(const lv_conv_args& a, cudaStream_t stream);
 int pick_ntile(int cout_pad);
 extern long long* g_timeline;
+extern int g_use_pdl;
 int head_bicubic_fwd(const float*, const float*, const float*, const float*, const float*, void*, float*, int, int, int, int,
                      int, cudaStream_t);
 int bicubic_x4(const float*, float*, int, int, int, int, cudaStream_t);
@@ -116,6 +118,12 @@ int lv_pack_conv3x3_weights(const lv_pack_item* items, int count, void* stream) 
 }
 
 int lv_conv3x3(const lv_conv_args* a, int max_ctas, void* stream) {
+  static const bool pdl_env = [] {
+    const char* e = getenv("LARVANET_B200_PDL");
+    if (e != nullptr) lv::g_use_pdl = (e[0] != '0');
+    return true;
+  }();
+  (void)pdl_env;
   int rc = check_conv(a);
   if (rc != LV_OK) return rc;
   if (a->dtype == LV_BF16) {

@@ -59,7 +59,10 @@ struct TcLaunch {
   int nres;    // number of prefetched epilogue inputs (mask, res1, res2 in that order)
 };
 
-template <int CIN, int NT, int NSTAGE>
+// EPI: compile-time description of the staged NHWC epilogue so that it is straight-line code (the compiler can batch all
+// shared-memory loads of a tile up front instead of serialising six small basic blocks): bit0 ReLU, bit1 ReLU-mask,
+// bit2 res1, bit3 res2; EPI < 0 = decide at run time (cold shapes / res_scale != 1).
+template <int CIN, int NT, int NSTAGE, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, const TcLaunch L) {
   using Cfg = TcCfg<CIN, NT, NSTAGE>;
@@ -102,6 +105,9 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the next conv of the chain may start its own prologue (barriers, TMEM, resident weights) on SMs that this
+  // grid has already vacated; it blocks in pdl_wait() before touching anything this grid writes.
+  pdl_launch_dependents();
 
   const int ntile = static_cast<int>(blockIdx.x % g.ntiles_n);  // fixed per CTA (grid is a multiple of ntiles_n)
   const int tiles_per_img = g.tiles_x * g.tiles_y;
@@ -123,6 +129,7 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
       pc_rc[i] = (idx < kHaloPix * Cfg::CH) ? ((r << 8) | col) : -1;
     }
     uint32_t fill = 0;      // running (tile, source) counter
+    pdl_wait();             // activations of the previous kernel are complete from here on
     for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
       const int pt = tile / g.ntiles_n;
       const int n = pt / tiles_per_img;
@@ -230,7 +237,11 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
     uint8_t* sOut = sEpi + eg * epi_bytes;
     uint8_t* sRes = sOut + Cfg::OUT_TILE;
     const bool tl0 = (threadIdx.x == 0);
-    const bool unit_scale = (a.res_scale == 1.0f);
+    const bool unit_scale = (EPI >= 0) || (a.res_scale == 1.0f);
+    const bool do_relu = (EPI >= 0) ? ((EPI & 1) != 0) : (a.relu != 0);
+    const bool do_mask = (EPI >= 0) ? ((EPI & 2) != 0) : (ri_mask >= 0);
+    const bool do_res1 = (EPI >= 0) ? ((EPI & 4) != 0) : (ri_res1 >= 0);
+    const bool do_res2 = (EPI >= 0) ? ((EPI & 8) != 0) : (ri_res2 >= 0);
     const uint32_t as = eg;
 
     auto decode = [&](int tile, int& n, int& ty0, int& tx0) {
@@ -260,6 +271,7 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
       cp_async_commit();
     };
 
+    pdl_wait();                               // residual/mask inputs and the output buffer belong to earlier kernels
     const int tile_stride = 2 * gridDim.x;
     uint32_t k = eg;                          // CTA-local tile counter (parity == accumulator stage)
     int tile = blockIdx.x + eg * gridDim.x;
@@ -288,44 +300,88 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
         if (nr > 0) cp_async_wait<0>();   // my pieces of this tile's residual rows have landed
         named_bar_sync(1 + eg, 128);      // A: all residual pieces visible; previous copy-out finished reading sOut
         if (tl0) tl_stamp(g, 3, k, 0);
-        const __nv_bfloat16* myres = reinterpret_cast<const __nv_bfloat16*>(sRes + m * kPitch);
-        __nv_bfloat16* myout = reinterpret_cast<__nv_bfloat16*>(sOut + m * kPitch);
-        const float* bias = sBias + ntile * NT;
+        if (eg == 0 && lane == 0) tl_stamp(g, 5 + q, k, 0);
+        // Shared-memory loads see ~300 clk latency while the MMAs of the other stage saturate the smem port, so each
+        // half-tile round first issues ALL its loads (bias + mask + residuals), then computes, then stores.
+        const uint8_t* __restrict__ myres = sRes + m * kPitch;
+        uint8_t* __restrict__ myout = sOut + m * kPitch;
+        const float* __restrict__ bias = sBias + ntile * NT;
+        constexpr int HC = NT / 2;           // channels per round
 #pragma unroll
-        for (int j = 0; j < NT / 8; ++j) {
-          float* vj = v + j * 8;
+        for (int hf = 0; hf < 2; ++hf) {
+          float* vh = v + hf * HC;
+          float4 bb[HC / 4];
+          uint4 qm[HC / 8], q1[HC / 8], q2[HC / 8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) vj[i] += bias[j * 8 + i];
+          for (int i = 0; i < HC / 4; ++i) bb[i] = reinterpret_cast<const float4*>(bias + hf * HC)[i];
+          if (do_mask) {
+#pragma unroll
+            for (int i = 0; i < HC / 8; ++i)
+              qm[i] = reinterpret_cast<const uint4*>(myres + ri_mask * Cfg::OUT_TILE + hf * HC * 2)[i];
+          }
+          if (do_res1) {
+#pragma unroll
+            for (int i = 0; i < HC / 8; ++i)
+              q1[i] = reinterpret_cast<const uint4*>(myres + ri_res1 * Cfg::OUT_TILE + hf * HC * 2)[i];
+          }
+          if (do_res2) {
+#pragma unroll
+            for (int i = 0; i < HC / 8; ++i)
+              q2[i] = reinterpret_cast<const uint4*>(myres + ri_res2 * Cfg::OUT_TILE + hf * HC * 2)[i];
+          }
+#pragma unroll
+          for (int i = 0; i < HC / 4; ++i) {
+            vh[4 * i + 0] += bb[i].x; vh[4 * i + 1] += bb[i].y; vh[4 * i + 2] += bb[i].z; vh[4 * i + 3] += bb[i].w;
+          }
           if (!unit_scale) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vj[i] *= a.res_scale;
+            for (int i = 0; i < HC; ++i) vh[i] *= a.res_scale;
           }
-          if (a.relu) {
+          if (do_relu) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vj[i] = fmaxf(vj[i], 0.f);
+            for (int i = 0; i < HC; ++i) vh[i] = fmaxf(vh[i], 0.f);
           }
-          if (ri_mask >= 0) {
-            float t[8];
-            load8(myres + ri_mask * (Cfg::OUT_TILE / 2) + j * 8, t);
+          if (do_mask) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vj[i] = (t[i] > 0.f) ? vj[i] : 0.f;
-          }
-          if (ri_res1 >= 0) {
-            float t[8];
-            load8(myres + ri_res1 * (Cfg::OUT_TILE / 2) + j * 8, t);
+            for (int i = 0; i < HC / 8; ++i) {
+              const uint32_t w4[4] = {qm[i].x, qm[i].y, qm[i].z, qm[i].w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vj[i] += t[i];
+              for (int e = 0; e < 4; ++e) {
+                vh[8 * i + 2 * e] = (bf16_lo(w4[e]) > 0.f) ? vh[8 * i + 2 * e] : 0.f;
+                vh[8 * i + 2 * e + 1] = (bf16_hi(w4[e]) > 0.f) ? vh[8 * i + 2 * e + 1] : 0.f;
+              }
+            }
           }
-          if (ri_res2 >= 0) {
-            float t[8];
-            load8(myres + ri_res2 * (Cfg::OUT_TILE / 2) + j * 8, t);
+          if (do_res1) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) vj[i] += t[i];
+            for (int i = 0; i < HC / 8; ++i) {
+              const uint32_t w4[4] = {q1[i].x, q1[i].y, q1[i].z, q1[i].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                vh[8 * i + 2 * e] += bf16_lo(w4[e]);
+                vh[8 * i + 2 * e + 1] += bf16_hi(w4[e]);
+              }
+            }
           }
-          store8(myout + j * 8, vj);
+          if (do_res2) {
+#pragma unroll
+            for (int i = 0; i < HC / 8; ++i) {
+              const uint32_t w4[4] = {q2[i].x, q2[i].y, q2[i].z, q2[i].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                vh[8 * i + 2 * e] += bf16_lo(w4[e]);
+                vh[8 * i + 2 * e + 1] += bf16_hi(w4[e]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < HC / 8; ++i)
+            store8(reinterpret_cast<__nv_bfloat16*>(myout + hf * HC * 2) + i * 8, vh + i * 8);
         }
+        if (eg == 0 && lane == 0) tl_stamp(g, 5 + q, k, 1);
         named_bar_sync(3 + eg, 128);      // B: tile staged in sOut; everyone is done reading sRes
         if (tl0) tl_stamp(g, 3, k, 2);
+        if (eg == 0 && lane == 0) tl_stamp(g, 5 + q, k, 2);
         if (nr > 0) prefetch_res(tile + tile_stride);   // next tile of this group, hidden behind the other group's turn
         // coalesced copy-out: consecutive threads write consecutive 16 B of a tile row
         {
@@ -377,13 +433,14 @@ int pick_ntile(int cout_pad) {
 }
 
 long long* g_timeline = nullptr;
+int g_use_pdl = 1;   // LARVANET_B200_PDL=0 switches programmatic dependent launch off (capi.cu reads the env var)
 constexpr size_t kMaxSmem = 227 * 1024;
 
-template <int CIN, int NT, int NSTAGE>
+template <int CIN, int NT, int NSTAGE, int EPI>
 static int launch_tc(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L, int max_ctas, cudaStream_t stream) {
   using Cfg = TcCfg<CIN, NT, NSTAGE>;
   const size_t smem = Cfg::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad);
-  auto kern = conv3x3_tc_kernel<CIN, NT, NSTAGE>;
+  auto kern = conv3x3_tc_kernel<CIN, NT, NSTAGE, EPI>;
   static size_t configured = 0;
   if (smem > configured) {
     LV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -393,20 +450,45 @@ static int launch_tc(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L
   if (ctas > g.total_tiles) ctas = g.total_tiles;
   ctas = (ctas / g.ntiles_n) * g.ntiles_n;
   if (ctas < g.ntiles_n) ctas = g.ntiles_n;
-  kern<<<static_cast<unsigned>(ctas), kTcThreads, smem, stream>>>(a, g, L);
-  LV_LAUNCH_OK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, g, L));
+  count_launch();
   return LV_OK;
 }
 
 // pick the deepest halo pipeline that fits in shared memory
 template <int CIN, int NT>
 static int dispatch_stages(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L, int max_ctas, cudaStream_t stream) {
-  if (TcCfg<CIN, NT, 4>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
-    return launch_tc<CIN, NT, 4>(a, g, L, max_ctas, stream);
+  if (TcCfg<CIN, NT, 4>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem) {
+    if constexpr (CIN == 48 && NT == 48) {
+      // the LarvaNet hot shape: straight-line epilogues for the flag combinations the engine uses
+      if (L.staged && a.res_scale == 1.0f) {
+        const int e = (a.relu ? 1 : 0) | (a.mask ? 2 : 0) | (a.res1 ? 4 : 0) | (a.res2 ? 8 : 0);
+        switch (e) {
+          case 0: return launch_tc<CIN, NT, 4, 0>(a, g, L, max_ctas, stream);
+          case 1: return launch_tc<CIN, NT, 4, 1>(a, g, L, max_ctas, stream);
+          case 2: return launch_tc<CIN, NT, 4, 2>(a, g, L, max_ctas, stream);
+          case 4: return launch_tc<CIN, NT, 4, 4>(a, g, L, max_ctas, stream);
+          case 12: return launch_tc<CIN, NT, 4, 12>(a, g, L, max_ctas, stream);
+          default: break;
+        }
+      }
+    }
+    return launch_tc<CIN, NT, 4, -1>(a, g, L, max_ctas, stream);
+  }
   if (TcCfg<CIN, NT, 3>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
-    return launch_tc<CIN, NT, 3>(a, g, L, max_ctas, stream);
+    return launch_tc<CIN, NT, 3, -1>(a, g, L, max_ctas, stream);
   if (TcCfg<CIN, NT, 2>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
-    return launch_tc<CIN, NT, 2>(a, g, L, max_ctas, stream);
+    return launch_tc<CIN, NT, 2, -1>(a, g, L, max_ctas, stream);
   set_error("conv3x3 tensor-core path: cin=%d x %d sources, cout tile %d does not fit in shared memory", CIN, a.num_src, NT);
   return LV_ERR_INVALID;
 }

@@ -239,6 +239,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ----
+// wait: blocks until every grid this one programmatically depends on has completed and flushed (no-op otherwise);
+// launch_dependents: lets the next PDL-launched grid start its prologue while this one is still running.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- TMEM allocation (one full warp executes these) ----
 template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");

@@ -20,20 +20,22 @@ def main():
     kw = dict(relu=True, res1=x) if mode == 'fwd' else {}
     for _ in range(3):
         ops.conv3x3([x], packed, 48, bias=b, out=o, max_ctas=ctas, **kw)
-    tl = torch.zeros(5 * 64 * 4, dtype=torch.int64, device='cuda')
+    tl = torch.zeros(9 * 64 * 4, dtype=torch.int64, device='cuda')
     lib.lv_debug_set_timeline(tl.data_ptr())
     ops.conv3x3([x], packed, 48, bias=b, out=o, max_ctas=ctas, **kw)
     torch.cuda.synchronize()
     lib.lv_debug_set_timeline(None)
-    t = tl.cpu().view(5, 64, 4)
+    t = tl.cpu().view(9, 64, 4)
     t0 = int(t[t > 0].min())
     names = {0: ('prod', ['wait_empty', 'got_empty', 'issued', 'arrived_full']),
              1: ('mma ', ['wait_tempty', 'got_tempty', 'got_full', 'committed']),
              2: ('epi ', ['wait_tfull', 'got_tfull', 'tmem_read', 'stored']),
              3: ('epi2', ['after_barA', 'got_res', 'after_barB', 'computed']),
-             4: ('epi3', ['fenced', 'loop_top', 'prefetched', '-'])}
+             4: ('epi3', ['fenced', 'loop_top', 'prefetched', '-']),
+             5: ('w0  ', ['afterA', 'computed', 'afterB', '-']), 6: ('w1  ', ['afterA', 'computed', 'afterB', '-']),
+             7: ('w2  ', ['afterA', 'computed', 'afterB', '-']), 8: ('w3  ', ['afterA', 'computed', 'afterB', '-'])}
     for k in range(6):
-        for role in range(5):
+        for role in range(9):
             nm, evs = names[role]
             vals = [int(t[role, k, e]) - t0 if t[role, k, e] > 0 else -1 for e in range(4)]
             print(f'tile {k:2d} {nm}: ' + '  '.join(f'{e}={v}' for e, v in zip(evs, vals)))
