@@ -509,3 +509,123 @@ class LarvaEngine:
         mf = self._act(n, h, w)
         self._conv(feats, 'tail.merge_conv', out=mf)
         return self._recon('tail', mf, base)
+
+
+class EdsrEngine:
+    """EDSR-baseline x2/x4 inference on the same conv kernels (reference models/edsr.py:177-207, BASELINE config 3):
+    1x1 mean_shift + first_conv in the head kernel, 2 convs per ResidualBlock (res_weight folded into the epilogue's
+    res_scale), after_res_conv with the global skip as residual, conv(F->4F) with a PixelShuffle(2) epilogue per
+    upsampling stage, final_conv(F->3) with the 1x1 mean_inverse_shift fused into its epilogue.  Inference only."""
+
+    def __init__(self, module, features, num_res_blocks, res_weight, scale, act_dtype=torch.bfloat16, device=None,
+                 use_graphs=None):
+        self.module = module
+        self.f = int(features)
+        self.nb = int(num_res_blocks)
+        self.res_weight = float(res_weight)
+        self.scale = int(scale)
+        if self.scale not in (2, 4, 8):
+            raise LarvaNetB200Error(f'EDSR scale {scale}: only the PixelShuffle(2) stages (x2/x4/x8) have a kernel')
+        self.nup = {2: 1, 4: 2, 8: 3}[self.scale]
+        self.act_dtype = act_dtype
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.sm_count = ops.device_check(self.device.index)
+        if act_dtype == torch.bfloat16 and self.f % 16 != 0:
+            raise LarvaNetB200Error(f'--edsr_conv_features={self.f}: the bf16 tensor-core path needs a multiple of 16 '
+                                    '(use --precision=fp32 for other widths)')
+        if use_graphs is None:
+            use_graphs = os.environ.get('LARVANET_B200_GRAPHS', '1') != '0'
+        self.use_graphs = use_graphs
+        self.arena = ParamArena(module, self.device)
+        self.simt = False
+        self.replayed_launches = 0
+        f = self.f
+        self._layers = [(f'res_blocks.{j}.body.{k}', f, f) for j in range(self.nb) for k in (0, 2)]
+        self._layers.append(('after_res_conv', f, f))
+        self._layers += [(f'upsample.body.{2 * s}', 4 * f, f) for s in range(self.nup)]
+        self._layers.append(('final_conv', 3, f))
+        sizes = [(p, ops.packed_weight_bytes(o, i, act_dtype)) for p, o, i in self._layers]
+        total = sum((b + 255) // 256 * 256 for _, b in sizes)
+        self._packed = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        self._pk, off = {}, 0
+        for p, b in sizes:
+            self._pk[p] = self._packed[off:off + b]
+            off += (b + 255) // 256 * 256
+        self._pack_items = [dict(w=self.arena.views[p + '.weight'], packed=self._pk[p], transpose=0, i_off=0, i_cnt=i,
+                                 cin=i, dtype=act_dtype) for p, o, i in self._layers]
+        self._packed_version = None
+        self._infer = {}
+
+    def repack(self, force=False):
+        ver = self.arena.version()
+        if force or ver != self._packed_version:
+            ops.pack_weights(self._pack_items)
+            self._packed_version = ver
+
+    def mark_weights_changed(self):
+        self._packed_version = None
+
+    def _conv(self, src, prefix, cout, **kw):
+        ops.conv3x3([src], self._pk[prefix], cout, bias=self.arena.views[prefix + '.bias'], simt=self.simt, **kw)
+
+    def _build(self, n, h, w):
+        b = _Bufs()
+        dev, dt, f = self.device, self.act_dtype, self.f
+        b.x = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
+        b.x0 = torch.empty((n, h, w, f), dtype=dt, device=dev)
+        b.t = torch.empty_like(b.x0)
+        b.pp = [torch.empty_like(b.x0), torch.empty_like(b.x0)]
+        b.up = [torch.empty((n, h << (s + 1), w << (s + 1), f), dtype=dt, device=dev) for s in range(self.nup)]
+        b.out = torch.empty((n, 3, h * self.scale, w * self.scale), dtype=torch.float32, device=dev)
+        return b
+
+    def _run(self, b):
+        v = self.arena.views
+        f = self.f
+        ops.head_bicubic(b.x, v['first_conv.weight'], v['first_conv.bias'], b.x0, None,
+                         pre_w=v['mean_shift.weight'], pre_b=v['mean_shift.bias'])
+        a = b.x0
+        for j in range(self.nb):
+            p = f'res_blocks.{j}.body'
+            self._conv(a, p + '.0', f, out=b.t, relu=True)
+            dst = b.pp[j & 1]
+            self._conv(b.t, p + '.2', f, out=dst, res1=a, res_scale=self.res_weight)
+            a = dst
+        skip = b.pp[self.nb & 1]
+        self._conv(a, 'after_res_conv', f, out=skip, res1=b.x0)
+        a = skip
+        for s in range(self.nup):
+            self._conv(a, f'upsample.body.{2 * s}', 4 * f, out=b.up[s], epilogue=_lib.LV_EPI_PS2_NHWC)
+            a = b.up[s]
+        self._conv(a, 'final_conv', 3, epilogue=_lib.LV_EPI_RGB_NCHW, out_hr=b.out,
+                   post_w=v['mean_inverse_shift.weight'], post_b=v['mean_inverse_shift.bias'])
+
+    def forward(self, x):
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise LarvaNetB200Error(f'expected NCHW input with 3 channels, got {tuple(x.shape)}')
+        n, _, h, w = (int(t) for t in x.shape)
+        self.repack()
+        key = (n, h, w)
+        ent = self._infer.get(key)
+        if ent is None:
+            ent = [self._build(n, h, w), None]
+            self._infer[key] = ent
+        b = ent[0]
+        b.x.copy_(x.to(dtype=torch.float32), non_blocking=True)
+        if n * h * w == 0:
+            return b.out
+        if self.use_graphs and not self.simt:
+            if ent[1] is None:
+                self._run(b)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                c0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    self._run(b)
+                ent[1] = g
+                ent.append(_lib.launch_count() - c0)
+            ent[1].replay()
+            self.replayed_launches += ent[2]
+        else:
+            self._run(b)
+        return b.out

@@ -218,3 +218,36 @@ def test_empty_and_ragged_inputs():
         assert np.max(np.abs(out - ref)) <= 2.0
     out = eng.forward(torch.zeros((0, 3, 8, 8), device='cuda'))
     assert out.shape == (0, 3, 32, 32)
+
+
+@pytest.mark.parametrize('name,precision', [('edsr_f64_b2', 'fp32'), ('edsr_f64_b2', 'bf16'), ('edsr_f16_b3', 'fp32')])
+def test_edsr_inference_matches_reference_golden(golden_dir, name, precision):
+    """EDSR-baseline forward (reference models/edsr.py:195-207) on the same conv kernels: 64->64, 64->256 +
+    PixelShuffle(2), 64->3 + fused 1x1 mean_inverse_shift, 1x1 mean_shift fused into the first conv."""
+    g = np.load(os.path.join(golden_dir, name + '.npz'))
+    feats, nb = int(g['features']), int(g['res_blocks'])
+    params = synth.make_edsr_params(feats, nb, 4, seed=int(g['seed']))
+    lr, _ = synth.make_images(int(g['n']), int(g['h']), int(g['w']), seed=int(g['seed']) + 100)
+    m = importlib.import_module('models.edsr').create_model()
+    m.parse_args([f'--edsr_conv_features={feats}', f'--edsr_res_blocks={nb}', f'--precision={precision}'])
+    m.prepare(is_training=False, scales=[4])
+    load_params(m.get_model(), params)
+    out = m.upscale(list(lr), 4)
+    ref = g['out_f32']
+    assert out.shape == ref.shape
+    if precision == 'fp32':
+        np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4 * max(1.0, float(np.abs(ref).max())))
+    else:
+        # EDSR's default-initialised (untrained) weights amplify: compare relative to the output's own scale
+        scale = float(np.abs(ref).max())
+        assert np.max(np.abs(out - ref)) <= max(2.0, 2.0 / 255.0 * scale), (np.max(np.abs(out - ref)), scale)
+    np.testing.assert_array_equal(out, m.upscale(list(lr), 4))
+    # cross-check the tensor-core chain against the CUDA-core chain on identical operands
+    if precision == 'bf16':
+        eng = m.get_model().engine()
+        x = torch.from_numpy(lr).cuda()
+        a = eng.forward(x).clone()
+        eng.simt = True
+        b = eng.forward(x).clone()
+        eng.simt = False
+        assert (a - b).abs().max().item() <= 1e-2 * max(1.0, float(b.abs().max()))

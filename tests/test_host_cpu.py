@@ -139,3 +139,17 @@ def test_chop_forward_split_and_combine_are_inverse_for_identity_model():
     img = np.random.RandomState(1).uniform(0, 255, (3, 22, 30))
     out = image_utils.upscale_with_chop_forward(Nearest(), img, scale=4, overlap_size=10)
     np.testing.assert_array_equal(out, np.repeat(np.repeat(img, 4, axis=1), 4, axis=2))
+
+
+def test_edsr_plugin_surface():
+    m = importlib.import_module('models.edsr').create_model()
+    args, rest = m.parse_args(['--edsr_res_blocks=3', '--edsr_conv_features=32', '--zzz'])
+    assert rest == ['--zzz'] and args.edsr_res_blocks == 3
+    m.prepare(is_training=False, scales=[4])
+    sd = m.get_model().state_dict()
+    shapes = synth.edsr_param_shapes(32, 3, 4)
+    assert list(sd.keys()) == list(shapes.keys())
+    assert all(tuple(sd[k].shape) == shapes[k] for k in shapes)
+    assert not m.get_model().mean_shift.weight.requires_grad       # frozen like the reference (models/edsr.py:135-136)
+    with pytest.raises(NotImplementedError):
+        m.train_step([], 4, [])
