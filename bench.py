@@ -176,7 +176,8 @@ def run_ours(a):
         raise SystemExit('bench.py needs a CUDA device: larvanet_b200 has no CPU path')
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        import datetime
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local), timeout=datetime.timedelta(seconds=120))
     dev = torch.device('cuda', local)
     peaks, peaks_src = measured_peaks()
 
@@ -265,14 +266,16 @@ def run_ours(a):
         'tflops_per_gpu': flops_train_per_patch() * BATCH / (ms / a.steps * 1e-3) / 1e12,
     }
 
+    # ---- instrumented pass: CUDA events around every conv launch of one eager training step.  Every rank runs it
+    # (the step contains the gradient all-reduce); rank 0 reports.
+    eng.use_graphs = False
+    ops.CONV_TIMERS = []
+    torch.cuda._sleep(int(4e7))   # ~20 ms of GPU spin so the host can queue the whole eager step ahead of the GPU:
+    step_resident(0)              # the events then bracket kernel time, not host launch latency
+    torch.cuda.synchronize()
+    recs, ops.CONV_TIMERS = ops.CONV_TIMERS, None
+    eng.use_graphs = True
     if rank == 0:
-        # ---- instrumented pass: CUDA events around every conv launch of one eager training step
-        eng.use_graphs = False
-        ops.CONV_TIMERS = []
-        step_resident(0)
-        torch.cuda.synchronize()
-        recs, ops.CONV_TIMERS = ops.CONV_TIMERS, None
-        eng.use_graphs = True
         durs = np.array([e0.elapsed_time(e1) for e0, e1, _, _ in recs]) * 1e-3
         fl = np.array([f for _, _, f, _ in recs])
         ach = float(fl.sum() / durs.sum() / 1e12)
