@@ -41,31 +41,30 @@ __device__ __forceinline__ float conv_epilogue16(const lv_conv_args& a, int n, i
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
   }
-  const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
   // 3. ReLU mask of the forward activation (backward-data through nn.ReLU)
   if (a.mask != nullptr) {
     float t[16];
-    load16(reinterpret_cast<const T*>(a.mask) + pix * C + co0, t);
+    load16_act(reinterpret_cast<const T*>(a.mask), n, y, x, co0, H, W, C, t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = (t[i] > 0.f) ? v[i] : 0.f;
   }
   // 4. residual / skip adds
   if (a.res1 != nullptr) {
     float t[16];
-    load16(reinterpret_cast<const T*>(a.res1) + pix * C + co0, t);
+    load16_act(reinterpret_cast<const T*>(a.res1), n, y, x, co0, H, W, C, t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += t[i];
   }
   if (a.res2 != nullptr) {
     float t[16];
-    load16(reinterpret_cast<const T*>(a.res2) + pix * C + co0, t);
+    load16_act(reinterpret_cast<const T*>(a.res2), n, y, x, co0, H, W, C, t);
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] += t[i];
   }
   float loss = 0.f;
   // 5. store
   if (a.epilogue == LV_EPI_NHWC) {
-    store16(reinterpret_cast<T*>(a.out) + pix * C + co0, v);
+    store16_act(reinterpret_cast<T*>(a.out), n, y, x, co0, H, W, C, v);
   } else if (a.epilogue == LV_EPI_PS4_NCHW) {
     const int c = co0 >> 4;
     const int CH = C >> 4;
@@ -91,18 +90,17 @@ __device__ __forceinline__ float conv_epilogue16(const lv_conv_args& a, int n, i
       }
     }
     if (a.truth_hr != nullptr && a.grad_sign != nullptr) {
-      store16(reinterpret_cast<T*>(a.grad_sign) + pix * C + co0, g);
+      store16_act(reinterpret_cast<T*>(a.grad_sign), n, y, x, co0, H, W, C, g);
     }
   } else if (a.epilogue == LV_EPI_PS2_NHWC) {
     const int CO = C >> 2;        // output channels after the shuffle
-    const int c0 = co0 >> 2;      // 4 consecutive output channels per chunk
+    const int c0 = co0 >> 2;      // 4 consecutive output channels per 16-channel input chunk (half of an 8-chunk)
     T* out = reinterpret_cast<T*>(a.out);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const size_t opix = (static_cast<size_t>(n) * (2 * H) + (2 * y + i)) * (2 * W) + (2 * x + j);
-        T* p = out + opix * CO + c0;
+        T* p = out + act_off(n, 2 * y + i, 2 * x + j, c0 >> 3, 2 * H, 2 * W, CO >> 3) + (c0 & 7);
 #pragma unroll
         for (int k = 0; k < 4; ++k) p[k] = from_f32<T>(v[4 * k + 2 * i + j]);
       }

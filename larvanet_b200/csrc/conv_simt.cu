@@ -44,7 +44,7 @@ conv3x3_simt_kernel(const __grid_constant__ lv_conv_args a, int tiles_x, int til
           const int gy = y0 - 1 + hp / kSHaloW, gx = x0 - 1 + hp % kSHaloW;
           float v = 0.f;
           if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w)
-            v = to_f32(src[((static_cast<size_t>(n) * a.h + gy) * a.w + gx) * cin + ci]);
+            v = to_f32(src[act_off(n, gy, gx, ci >> 3, a.h, a.w, cin >> 3) + (ci & 7)]);
           sx[hp * cinp + ci] = v;
         }
         __syncthreads();
@@ -108,7 +108,7 @@ int conv3x3_simt(const lv_conv_args& a, cudaStream_t stream) {
   const long long blocks = static_cast<long long>(a.n) * tiles_x * tiles_y;
   if (blocks == 0) return LV_OK;
   LV_CHECK_ARG(blocks < (1ll << 31), "conv3x3: too many tiles");
-  LV_CHECK_ARG(a.cin <= 64, "conv3x3 CUDA-core path supports cin <= 64 per source (got %d)", a.cin);
+  LV_CHECK_ARG(a.cin <= 64 && a.cin % 8 == 0, "conv3x3 CUDA-core path supports cin <= 64, multiple of 8 (got %d)", a.cin);
   const size_t smem = static_cast<size_t>(kSHaloPix) * (a.cin + 1) * sizeof(float);
   const int cout_pad = (a.cout + 15) / 16 * 16;
   if (a.dtype == LV_F32) {

@@ -9,20 +9,21 @@
 // no im2col, no per-tap copies, zero padding comes from zero-filled halo pixels.  (Measured on B200: the cost of one
 // M=128,K=16 SS MMA is max(N/2, 32+N/4) cycles and does NOT depend on swizzle mode or operand alignment.)
 //
+// Activations live in HBM in the planar-8 layout [N][H][C/8][W][8] (lv_common.cuh): a halo row of one chunk is one
+// contiguous 160 B run (coalesced cp.async, conflict-free shared-memory writes), and the epilogue -- one output pixel
+// per thread, a warp = 4 tile rows x 8 pixels -- reads residuals and writes results as four full 128 B lines per
+// 8-channel chunk straight from registers.  No shared-memory staging: shared-memory bandwidth is the bounding
+// resource of this kernel (one N=48 MMA = 45 clk = its 5.5 KB of operand reads at 128 B/clk), so the epilogue stays
+// off it entirely.
+//
 // Weights (bf16, pre-packed as [ntile][src][tap][chunk][cout][8]) stay resident in shared memory for the whole
 // persistent CTA; they arrive with one TMA bulk copy per (src,tap) block.
 //
-// Warp roles (416 threads): warps 0-3 = epilogue group 0, warps 4-7 = epilogue group 1 (warp w reads TMEM lane quarter
-// w%4), warp 8 TMEM alloc + MMA issue by one elected lane, warps 9-12 halo-tile producers (cp.async 16 B, zero-fill
-// outside the image).  The CTA's tiles alternate between the two TMEM accumulator stages; stage s is always drained by
-// epilogue group s, so two epilogues and one MMA phase are in flight at any time.
-//
-// Shared memory bandwidth is the bounding resource of this kernel (measured: one M=128,N=48,K=16 SS MMA = 45 cycles =
-// its 5.5 KB of operand reads at 128 B/clk), so everything else is arranged to stay out of its way:
-// Epilogue (NHWC outputs): each group prefetches the residual / skip / ReLU-mask tile of its NEXT tile with cp.async
-// while the MMAs run, adds bias/ReLU/mask/residuals in registers, stages the bf16 tile as dense NHWC rows in shared
-// memory and copies it out with fully coalesced 16 B stores -- no epilogue thread waits on global memory.
-// PixelShuffle / RGB epilogues keep the direct per-thread path (their stores are already full 128 B lines).
+// Warp roles (384 threads): warps 0-3 = epilogue group 0, warps 4-7 = epilogue group 1 (warp w reads TMEM lane quarter
+// w%4), warp 8 TMEM alloc + MMA issue by one elected lane, warps 9-11 halo-tile producers.  The CTA's tiles alternate
+// between the two TMEM accumulator stages; stage s is always drained by epilogue group s, so two epilogues and one MMA
+// phase are in flight at any time.  Launched with programmatic dependent launch: the next conv's prologue overlaps
+// this one's tail.
 #include "conv_epilogue.cuh"
 #include "lv_common.cuh"
 
@@ -30,41 +31,31 @@ namespace lv {
 
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2, kHaloPix = kHaloW * kHaloH;  // 10 x 18 = 180
-constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 128;
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 96;
 constexpr int kMmaWarp = kEpiWarps;                           // warp 8
-constexpr int kTcThreads = kEpiThreads + 32 + kProdThreads;  // 416
-constexpr int kMaxRes = 3;                                    // mask, res1, res2
+constexpr int kTcThreads = kEpiThreads + 32 + kProdThreads;  // 384 (<= 168 registers per thread)
 
 template <int CIN, int NT, int NSTAGE>
 struct TcCfg {
   static constexpr int CH = CIN / 8;                    // 16-byte channel chunks per pixel
   static constexpr int KSTEPS = CIN / 16;               // UMMA K steps per tap
-  static constexpr int A_PLANE = kHaloPix * 16 + 16;    // bytes of one chunk plane (+16: spreads cp.async banks)
+  static constexpr int A_PLANE = kHaloPix * 16;         // bytes of one chunk plane
   static constexpr int A_STAGE = CH * A_PLANE;
   static constexpr int W_TAP = CH * NT * 16;            // bytes of one (src,tap) weight block
   static constexpr int ACC_STRIDE = (NT <= 64) ? 64 : 128;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int LAG = (NSTAGE >= 3) ? 2 : 1;     // cp.async groups kept in flight per producer thread
-  static constexpr int PIX_PITCH = NT * 2 + 16;         // staged pixel pitch (+16 B: conflict-free 16 B accesses)
-  static constexpr int OUT_TILE = 128 * PIX_PITCH;      // bytes of one staged NHWC tile (bf16)
   static constexpr int PROD_PIECES = (kHaloPix * CH + kProdThreads - 1) / kProdThreads;
-  static size_t smem_bytes(int num_src, int staged, int nres, int cout_pad) {
+  static size_t smem_bytes(int num_src, int cout_pad) {
     return static_cast<size_t>(num_src) * 9 * W_TAP + static_cast<size_t>(NSTAGE) * A_STAGE +
-           (staged ? static_cast<size_t>(2) * (1 + nres) * OUT_TILE : 0) + static_cast<size_t>(cout_pad) * 4 + 256;
+           static_cast<size_t>(cout_pad) * 4 + 256;
   }
 };
 
-struct TcLaunch {
-  int staged;  // NHWC epilogue through shared memory + TMA bulk stores
-  int nres;    // number of prefetched epilogue inputs (mask, res1, res2 in that order)
-};
-
-// EPI: compile-time description of the staged NHWC epilogue so that it is straight-line code (the compiler can batch all
-// shared-memory loads of a tile up front instead of serialising six small basic blocks): bit0 ReLU, bit1 ReLU-mask,
-// bit2 res1, bit3 res2; EPI < 0 = decide at run time (cold shapes / res_scale != 1).
+// EPI: compile-time description of the fast planar epilogue so that it is straight-line code: bit0 ReLU,
+// bit1 ReLU-mask, bit2 res1, bit3 res2; EPI < 0 = decide at run time (cold shapes / res_scale != 1).
 template <int CIN, int NT, int NSTAGE, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, const TcLaunch L) {
+conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
   using Cfg = TcCfg<CIN, NT, NSTAGE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -73,9 +64,7 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
   const uint32_t w_bytes = static_cast<uint32_t>(a.num_src) * 9u * Cfg::W_TAP;
   uint8_t* sW = smem;
   uint8_t* sA = sW + w_bytes;
-  uint8_t* sEpi = sA + NSTAGE * Cfg::A_STAGE;  // per epilogue group: [out tile][nres residual tiles]
-  const int epi_bytes = L.staged ? (1 + L.nres) * Cfg::OUT_TILE : 0;
-  float* sBias = reinterpret_cast<float*>(sEpi + 2 * epi_bytes);
+  float* sBias = reinterpret_cast<float*>(sA + NSTAGE * Cfg::A_STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + g.cout_pad);
   // bars: [0,NSTAGE) full, [NSTAGE,2NSTAGE) empty, then tmem_full[2], tmem_empty[2], wbar
   const uint32_t bar0 = smem_u32(bars);
@@ -115,17 +104,18 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
   if (warp > kMmaWarp) {
     // =============================== producers: halo tiles -> smem ===============================
     const int ptid = threadIdx.x - (kEpiThreads + 32);
-    // tile-invariant description of this thread's 16 B pieces of a halo tile
+    // tile-invariant description of this thread's 16 B pieces of a halo tile; piece index = ((row*CH + chunk)*10 + col):
+    // consecutive lanes copy consecutive 16 B of one contiguous 160 B global run to consecutive 16 B of one plane
     uint32_t pc_dst[Cfg::PROD_PIECES];   // smem offset inside a stage
-    int pc_rel[Cfg::PROD_PIECES];        // element offset relative to the halo origin pixel
+    int pc_rel[Cfg::PROD_PIECES];        // element offset relative to the halo origin (row y0, chunk 0, column x0)
     int pc_rc[Cfg::PROD_PIECES];         // (row << 8) | col inside the halo, -1 = no piece
 #pragma unroll
     for (int i = 0; i < Cfg::PROD_PIECES; ++i) {
       const int idx = ptid + i * kProdThreads;
-      const int p = idx / Cfg::CH, c = idx - p * Cfg::CH;
-      const int r = p / kHaloW, col = p - r * kHaloW;
-      pc_dst[i] = c * Cfg::A_PLANE + p * 16;
-      pc_rel[i] = (r * a.w + col) * CIN + c * 8;
+      const int col = idx % kHaloW, rc = idx / kHaloW;
+      const int c = rc % Cfg::CH, r = rc / Cfg::CH;
+      pc_dst[i] = c * Cfg::A_PLANE + (r * kHaloW + col) * 16;
+      pc_rel[i] = ((r * Cfg::CH + c) * a.w + col) * 8;
       pc_rc[i] = (idx < kHaloPix * Cfg::CH) ? ((r << 8) | col) : -1;
     }
     uint32_t fill = 0;      // running (tile, source) counter
@@ -137,7 +127,7 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
       const int ty = rem / g.tiles_x;
       const int y0 = ty * kTileH - 1;
       const int x0 = (rem - ty * g.tiles_x) * kTileW - 1;
-      const long long origin = ((static_cast<long long>(n) * a.h + y0) * a.w + x0) * CIN;
+      const long long origin = ((static_cast<long long>(n) * a.h + y0) * Cfg::CH * a.w + x0) * 8;
       for (int s = 0; s < a.num_src; ++s, ++fill) {
         const int stage = fill % NSTAGE;
         if (ptid == 0) tl_stamp(g, 0, fill, 0);
@@ -165,7 +155,8 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer (one elected lane) ================================
     if (elect_one()) {  // elect.sync: lets the compiler prove single-lane execution (no per-MMA lane waterfall)
-      // resident weights: one bulk copy per (src,tap) block
+      // resident weights: one bulk copy per (src,tap) block (weights/bias are never written inside a launch chain,
+      // so this may run before pdl_wait)
       mbar_arrive_expect_tx(wbar, w_bytes);
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.weights) + static_cast<size_t>(ntile) * w_bytes;
       for (int b = 0; b < a.num_src * 9; ++b)
@@ -210,193 +201,139 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
     }
     __syncwarp();
   } else {
-    // =============================== epilogue: TMEM -> registers -> (smem ->) global ==============
+    // =============================== epilogue: TMEM -> registers -> global ========================
     const int eg = warp >> 2, q = warp & 3;  // epilogue group == TMEM accumulator stage, TMEM lane quarter
     const int m = q * 32 + lane;             // TMEM lane == tile pixel index == thread index within the group
     const int r = m >> 3, c = m & 7;
     float loss = 0.f;
-    const void* rp[kMaxRes] = {nullptr, nullptr, nullptr};
-    int ri_mask = -1, ri_res1 = -1, ri_res2 = -1, nr = 0;
-    if (a.mask != nullptr) { rp[nr] = a.mask; ri_mask = nr++; }
-    if (a.res1 != nullptr) { rp[nr] = a.res1; ri_res1 = nr++; }
-    if (a.res2 != nullptr) { rp[nr] = a.res2; ri_res2 = nr++; }
-    constexpr int kPitch = Cfg::PIX_PITCH;       // staged pixel pitch in bytes
-    constexpr int kPieces = 128 * NT / 8 / 128;  // 16 B pieces per thread per tile (= NT/8)
-    // tile-invariant description of this thread's pieces for the coalesced copy-out / residual prefetch:
-    // piece pc = m + 128*i  ->  pixel pc/(NT/8) of the tile, channel chunk pc%(NT/8)
-    uint32_t ep_smem[kPieces];
-    int ep_rel[kPieces], ep_rc[kPieces];
-#pragma unroll
-    for (int i = 0; i < kPieces; ++i) {
-      const int pc = m + 128 * i;
-      const int px = pc / (NT / 8), ch = pc - px * (NT / 8);
-      ep_smem[i] = px * kPitch + ch * 16;
-      ep_rel[i] = ((px >> 3) * a.w + (px & 7)) * NT + ch * 8;
-      ep_rc[i] = ((px >> 3) << 8) | (px & 7);
-    }
-    uint8_t* sOut = sEpi + eg * epi_bytes;
-    uint8_t* sRes = sOut + Cfg::OUT_TILE;
     const bool tl0 = (threadIdx.x == 0);
+    constexpr bool kFastShape = (NT <= 64);
+    const bool fast = kFastShape && (a.epilogue == LV_EPI_NHWC) && (a.cout == g.cout_pad);
     const bool unit_scale = (EPI >= 0) || (a.res_scale == 1.0f);
     const bool do_relu = (EPI >= 0) ? ((EPI & 1) != 0) : (a.relu != 0);
-    const bool do_mask = (EPI >= 0) ? ((EPI & 2) != 0) : (ri_mask >= 0);
-    const bool do_res1 = (EPI >= 0) ? ((EPI & 4) != 0) : (ri_res1 >= 0);
-    const bool do_res2 = (EPI >= 0) ? ((EPI & 8) != 0) : (ri_res2 >= 0);
+    const bool do_mask = (EPI >= 0) ? ((EPI & 2) != 0) : (a.mask != nullptr);
+    const bool do_res1 = (EPI >= 0) ? ((EPI & 4) != 0) : (a.res1 != nullptr);
+    const bool do_res2 = (EPI >= 0) ? ((EPI & 8) != 0) : (a.res2 != nullptr);
     const uint32_t as = eg;
+    constexpr int NCH = kFastShape ? NT / 8 : 1;   // 8-channel chunks per thread on the fast path
+    const int CHo = g.cout_pad >> 3;               // chunks per pixel of the output tensor
+    const size_t chunk_stride = static_cast<size_t>(a.w) * 8;   // elements between consecutive chunks of a pixel
 
-    auto decode = [&](int tile, int& n, int& ty0, int& tx0) {
-      const int pt = tile / g.ntiles_n;
-      n = pt / tiles_per_img;
-      const int rem = pt - n * tiles_per_img;
-      const int tyi = rem / g.tiles_x;
-      ty0 = tyi * kTileH;
-      tx0 = (rem - tyi * g.tiles_x) * kTileW;
-    };
-    // cp.async the mask/residual tiles of `tile` into this group's sRes (dense NHWC rows, 16 B pieces, coalesced)
-    auto prefetch_res = [&](int tile) {
-      if (tile < g.total_tiles) {
-        int n, ty0, tx0;
-        decode(tile, n, ty0, tx0);
-        const long long origin = ((static_cast<long long>(n) * a.h + ty0) * a.w + tx0) * NT;
-        const int vh = a.h - ty0, vw = a.w - tx0;
-        for (int i = 0; i < nr; ++i) {
-          const __nv_bfloat16* gsrc = reinterpret_cast<const __nv_bfloat16*>(rp[i]) + origin;
-          const uint32_t dst = smem_u32(sRes + i * Cfg::OUT_TILE);
+    // bias lives in registers for the whole CTA: the epilogue must not touch shared memory (the MMAs saturate it and
+    // an LDS then takes ~300 clk)
+    float breg[kFastShape ? NT : 1];
+    if constexpr (kFastShape) {
 #pragma unroll
-          for (int j = 0; j < kPieces; ++j) {
-            if ((ep_rc[j] >> 8) < vh && (ep_rc[j] & 0xff) < vw) cp_async16(dst + ep_smem[j], gsrc + ep_rel[j], 16u);
-          }
-        }
-      }
-      cp_async_commit();
-    };
-
+      for (int i = 0; i < NT; ++i) breg[i] = sBias[ntile * NT + i];
+    }
     pdl_wait();                               // residual/mask inputs and the output buffer belong to earlier kernels
     const int tile_stride = 2 * gridDim.x;
     uint32_t k = eg;                          // CTA-local tile counter (parity == accumulator stage)
-    int tile = blockIdx.x + eg * gridDim.x;
-    if (L.staged && nr > 0) prefetch_res(tile);
-
-    for (; tile < g.total_tiles; tile += tile_stride, k += 2) {
-      int n, ty0, tx0;
-      decode(tile, n, ty0, tx0);
-      const int y = ty0 + r, x = tx0 + c;
+    for (int tile = blockIdx.x + eg * gridDim.x; tile < g.total_tiles; tile += tile_stride, k += 2) {
+      const int pt = tile / g.ntiles_n;
+      const int n = pt / tiles_per_img;
+      const int rem = pt - n * tiles_per_img;
+      const int tyi = rem / g.tiles_x;
+      const int y = tyi * kTileH + r, x = (rem - tyi * g.tiles_x) * kTileW + c;
       const bool valid = (y < a.h) && (x < a.w);
-
-      if (tl0) tl_stamp(g, 2, k, 0);
-      mbar_wait_relaxed(tfull_bar(as), (k >> 1) & 1);
-      tc_fence_after_sync();
-      if (tl0) tl_stamp(g, 2, k, 1);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 
-      if (L.staged) {
-        float v[NT];
+      if (fast) {
+        if constexpr (kFastShape) {
+          // element offset of this pixel's first output chunk; all epilogue operands share the output geometry
+          const size_t o0 = valid ? act_off(n, y, x, ntile * (NT / 8), a.h, a.w, CHo) : 0;
+          // issue every global load of the tile BEFORE waiting for the accumulator: their latency hides behind the MMAs
+          uint4 qm[NCH], q1[NCH], q2[NCH];
+          if (valid) {
+            if (do_mask) {
+              const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.mask) + o0;
 #pragma unroll
-        for (int j = 0; j < NT / 16; ++j) tmem_ld16(taddr + j * 16, v + j * 16);
-        tmem_ld_wait();
-        tc_fence_before_sync();
-        mbar_arrive(tempty_bar(as));      // accumulator stage free: this group's next tile may be accumulated
-        if (tl0) tl_stamp(g, 2, k, 2);
-        if (nr > 0) cp_async_wait<0>();   // my pieces of this tile's residual rows have landed
-        named_bar_sync(1 + eg, 128);      // A: all residual pieces visible; previous copy-out finished reading sOut
-        if (tl0) tl_stamp(g, 3, k, 0);
-        if (eg == 0 && lane == 0) tl_stamp(g, 5 + q, k, 0);
-        // Shared-memory loads see ~300 clk latency while the MMAs of the other stage saturate the smem port, so each
-        // half-tile round first issues ALL its loads (bias + mask + residuals), then computes, then stores.
-        const uint8_t* __restrict__ myres = sRes + m * kPitch;
-        uint8_t* __restrict__ myout = sOut + m * kPitch;
-        const float* __restrict__ bias = sBias + ntile * NT;
-        constexpr int HC = NT / 2;           // channels per round
+              for (int j = 0; j < NCH; ++j) qm[j] = *reinterpret_cast<const uint4*>(p + j * chunk_stride);
+            }
+            if (do_res1) {
+              const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.res1) + o0;
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float* vh = v + hf * HC;
-          float4 bb[HC / 4];
-          uint4 qm[HC / 8], q1[HC / 8], q2[HC / 8];
+              for (int j = 0; j < NCH; ++j) q1[j] = *reinterpret_cast<const uint4*>(p + j * chunk_stride);
+            }
+            if (do_res2) {
+              const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(a.res2) + o0;
 #pragma unroll
-          for (int i = 0; i < HC / 4; ++i) bb[i] = reinterpret_cast<const float4*>(bias + hf * HC)[i];
-          if (do_mask) {
-#pragma unroll
-            for (int i = 0; i < HC / 8; ++i)
-              qm[i] = reinterpret_cast<const uint4*>(myres + ri_mask * Cfg::OUT_TILE + hf * HC * 2)[i];
+              for (int j = 0; j < NCH; ++j) q2[j] = *reinterpret_cast<const uint4*>(p + j * chunk_stride);
+            }
           }
-          if (do_res1) {
+          // pull the NEXT tile's residual/mask lines of this group into L2 while this tile is processed
+          {
+            const int tile2 = tile + tile_stride;
+            if (tile2 < g.total_tiles && (do_mask || do_res1 || do_res2)) {
+              const int pt2 = tile2 / g.ntiles_n;
+              const int n2 = pt2 / tiles_per_img;
+              const int rem2 = pt2 - n2 * tiles_per_img;
+              const int ty2 = rem2 / g.tiles_x;
+              const int y2 = ty2 * kTileH + r, x2 = (rem2 - ty2 * g.tiles_x) * kTileW + c;
+              if (y2 < a.h && x2 < a.w) {
+                const size_t o2 = act_off(n2, y2, x2, ntile * (NT / 8), a.h, a.w, CHo);
 #pragma unroll
-            for (int i = 0; i < HC / 8; ++i)
-              q1[i] = reinterpret_cast<const uint4*>(myres + ri_res1 * Cfg::OUT_TILE + hf * HC * 2)[i];
-          }
-          if (do_res2) {
-#pragma unroll
-            for (int i = 0; i < HC / 8; ++i)
-              q2[i] = reinterpret_cast<const uint4*>(myres + ri_res2 * Cfg::OUT_TILE + hf * HC * 2)[i];
-          }
-#pragma unroll
-          for (int i = 0; i < HC / 4; ++i) {
-            vh[4 * i + 0] += bb[i].x; vh[4 * i + 1] += bb[i].y; vh[4 * i + 2] += bb[i].z; vh[4 * i + 3] += bb[i].w;
-          }
-          if (!unit_scale) {
-#pragma unroll
-            for (int i = 0; i < HC; ++i) vh[i] *= a.res_scale;
-          }
-          if (do_relu) {
-#pragma unroll
-            for (int i = 0; i < HC; ++i) vh[i] = fmaxf(vh[i], 0.f);
-          }
-          if (do_mask) {
-#pragma unroll
-            for (int i = 0; i < HC / 8; ++i) {
-              const uint32_t w4[4] = {qm[i].x, qm[i].y, qm[i].z, qm[i].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                vh[8 * i + 2 * e] = (bf16_lo(w4[e]) > 0.f) ? vh[8 * i + 2 * e] : 0.f;
-                vh[8 * i + 2 * e + 1] = (bf16_hi(w4[e]) > 0.f) ? vh[8 * i + 2 * e + 1] : 0.f;
+                for (int j = 0; j < NCH; ++j) {
+                  if (do_mask) prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.mask) + o2 + j * chunk_stride);
+                  if (do_res1) prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.res1) + o2 + j * chunk_stride);
+                  if (do_res2) prefetch_l2(reinterpret_cast<const __nv_bfloat16*>(a.res2) + o2 + j * chunk_stride);
+                }
               }
             }
           }
-          if (do_res1) {
+          if (tl0) tl_stamp(g, 2, k, 0);
+          mbar_wait_relaxed(tfull_bar(as), (k >> 1) & 1);
+          tc_fence_after_sync();
+          if (tl0) tl_stamp(g, 2, k, 1);
+          float v[NT];
 #pragma unroll
-            for (int i = 0; i < HC / 8; ++i) {
-              const uint32_t w4[4] = {q1[i].x, q1[i].y, q1[i].z, q1[i].w};
+          for (int j = 0; j < NT / 16; ++j) tmem_ld16(taddr + j * 16, v + j * 16);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          mbar_arrive(tempty_bar(as));      // accumulator stage free: this group's next tile may be accumulated
+          if (tl0) tl_stamp(g, 2, k, 2);
+          if (valid) {
+            __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(a.out) + o0;
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                vh[8 * i + 2 * e] += bf16_lo(w4[e]);
-                vh[8 * i + 2 * e + 1] += bf16_hi(w4[e]);
+            for (int j = 0; j < NCH; ++j) {
+              float* vj = v + 8 * j;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vj[i] += breg[8 * j + i];
+              if (!unit_scale) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vj[i] *= a.res_scale;
               }
+              if (do_relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vj[i] = fmaxf(vj[i], 0.f);
+              }
+              if (do_mask) {
+                const uint32_t w4[4] = {qm[j].x, qm[j].y, qm[j].z, qm[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  vj[2 * e] = (bf16_lo(w4[e]) > 0.f) ? vj[2 * e] : 0.f;
+                  vj[2 * e + 1] = (bf16_hi(w4[e]) > 0.f) ? vj[2 * e + 1] : 0.f;
+                }
+              }
+              if (do_res1) {
+                const uint32_t w4[4] = {q1[j].x, q1[j].y, q1[j].z, q1[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { vj[2 * e] += bf16_lo(w4[e]); vj[2 * e + 1] += bf16_hi(w4[e]); }
+              }
+              if (do_res2) {
+                const uint32_t w4[4] = {q2[j].x, q2[j].y, q2[j].z, q2[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { vj[2 * e] += bf16_lo(w4[e]); vj[2 * e + 1] += bf16_hi(w4[e]); }
+              }
+              store8(po + j * chunk_stride, vj);   // a warp writes four full 128 B lines per chunk
             }
           }
-          if (do_res2) {
-#pragma unroll
-            for (int i = 0; i < HC / 8; ++i) {
-              const uint32_t w4[4] = {q2[i].x, q2[i].y, q2[i].z, q2[i].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                vh[8 * i + 2 * e] += bf16_lo(w4[e]);
-                vh[8 * i + 2 * e + 1] += bf16_hi(w4[e]);
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < HC / 8; ++i)
-            store8(reinterpret_cast<__nv_bfloat16*>(myout + hf * HC * 2) + i * 8, vh + i * 8);
+          if (tl0) tl_stamp(g, 2, k, 3);
         }
-        if (eg == 0 && lane == 0) tl_stamp(g, 5 + q, k, 1);
-        named_bar_sync(3 + eg, 128);      // B: tile staged in sOut; everyone is done reading sRes
-        if (tl0) tl_stamp(g, 3, k, 2);
-        if (eg == 0 && lane == 0) tl_stamp(g, 5 + q, k, 2);
-        if (nr > 0) prefetch_res(tile + tile_stride);   // next tile of this group, hidden behind the other group's turn
-        // coalesced copy-out: consecutive threads write consecutive 16 B of a tile row
-        {
-          __nv_bfloat16* gout = reinterpret_cast<__nv_bfloat16*>(a.out) +
-                                ((static_cast<long long>(n) * a.h + ty0) * a.w + tx0) * NT;
-          const int vh = a.h - ty0, vw = a.w - tx0;
-#pragma unroll
-          for (int j = 0; j < kPieces; ++j) {
-            if ((ep_rc[j] >> 8) < vh && (ep_rc[j] & 0xff) < vw)
-              *reinterpret_cast<uint4*>(gout + ep_rel[j]) = *reinterpret_cast<const uint4*>(sOut + ep_smem[j]);
-          }
-        }
-        if (tl0) tl_stamp(g, 2, k, 3);
       } else {
-        // direct path (PixelShuffle / RGB / multi-N-tile epilogues)
+        // generic path (PixelShuffle / RGB / multi-N-tile / cold shapes): shared 16-channel epilogue
+        mbar_wait_relaxed(tfull_bar(as), (k >> 1) & 1);
+        tc_fence_after_sync();
 #pragma unroll 1
         for (int j = 0; j < NT / 16; ++j) {
           float v[16];
@@ -408,7 +345,6 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g, cons
         mbar_arrive(tempty_bar(as));
       }
     }
-    if (L.staged && nr > 0) cp_async_wait<0>();
     if (a.truth_hr != nullptr && a.loss_sum != nullptr) {
       loss = warp_sum(loss);
       if (lane == 0) atomicAdd(a.loss_sum, static_cast<double>(loss));
@@ -437,9 +373,9 @@ int g_use_pdl = 1;   // LARVANET_B200_PDL=0 switches programmatic dependent laun
 constexpr size_t kMaxSmem = 227 * 1024;
 
 template <int CIN, int NT, int NSTAGE, int EPI>
-static int launch_tc(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L, int max_ctas, cudaStream_t stream) {
+static int launch_tc(const lv_conv_args& a, const ConvGeom& g, int max_ctas, cudaStream_t stream) {
   using Cfg = TcCfg<CIN, NT, NSTAGE>;
-  const size_t smem = Cfg::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad);
+  const size_t smem = Cfg::smem_bytes(a.num_src, g.cout_pad);
   auto kern = conv3x3_tc_kernel<CIN, NT, NSTAGE, EPI>;
   static size_t configured = 0;
   if (smem > configured) {
@@ -460,35 +396,35 @@ static int launch_tc(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, g, L));
+  LV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, g));
   count_launch();
   return LV_OK;
 }
 
 // pick the deepest halo pipeline that fits in shared memory
 template <int CIN, int NT>
-static int dispatch_stages(const lv_conv_args& a, const ConvGeom& g, const TcLaunch& L, int max_ctas, cudaStream_t stream) {
-  if (TcCfg<CIN, NT, 4>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem) {
+static int dispatch_stages(const lv_conv_args& a, const ConvGeom& g, int max_ctas, cudaStream_t stream) {
+  if (TcCfg<CIN, NT, 4>::smem_bytes(a.num_src, g.cout_pad) <= kMaxSmem) {
     if constexpr (CIN == 48 && NT == 48) {
       // the LarvaNet hot shape: straight-line epilogues for the flag combinations the engine uses
-      if (L.staged && a.res_scale == 1.0f) {
+      if (a.epilogue == LV_EPI_NHWC && a.res_scale == 1.0f) {
         const int e = (a.relu ? 1 : 0) | (a.mask ? 2 : 0) | (a.res1 ? 4 : 0) | (a.res2 ? 8 : 0);
         switch (e) {
-          case 0: return launch_tc<CIN, NT, 4, 0>(a, g, L, max_ctas, stream);
-          case 1: return launch_tc<CIN, NT, 4, 1>(a, g, L, max_ctas, stream);
-          case 2: return launch_tc<CIN, NT, 4, 2>(a, g, L, max_ctas, stream);
-          case 4: return launch_tc<CIN, NT, 4, 4>(a, g, L, max_ctas, stream);
-          case 12: return launch_tc<CIN, NT, 4, 12>(a, g, L, max_ctas, stream);
+          case 0: return launch_tc<CIN, NT, 4, 0>(a, g, max_ctas, stream);
+          case 1: return launch_tc<CIN, NT, 4, 1>(a, g, max_ctas, stream);
+          case 2: return launch_tc<CIN, NT, 4, 2>(a, g, max_ctas, stream);
+          case 4: return launch_tc<CIN, NT, 4, 4>(a, g, max_ctas, stream);
+          case 12: return launch_tc<CIN, NT, 4, 12>(a, g, max_ctas, stream);
           default: break;
         }
       }
     }
-    return launch_tc<CIN, NT, 4, -1>(a, g, L, max_ctas, stream);
+    return launch_tc<CIN, NT, 4, -1>(a, g, max_ctas, stream);
   }
-  if (TcCfg<CIN, NT, 3>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
-    return launch_tc<CIN, NT, 3, -1>(a, g, L, max_ctas, stream);
-  if (TcCfg<CIN, NT, 2>::smem_bytes(a.num_src, L.staged, L.nres, g.cout_pad) <= kMaxSmem)
-    return launch_tc<CIN, NT, 2, -1>(a, g, L, max_ctas, stream);
+  if (TcCfg<CIN, NT, 3>::smem_bytes(a.num_src, g.cout_pad) <= kMaxSmem)
+    return launch_tc<CIN, NT, 3, -1>(a, g, max_ctas, stream);
+  if (TcCfg<CIN, NT, 2>::smem_bytes(a.num_src, g.cout_pad) <= kMaxSmem)
+    return launch_tc<CIN, NT, 2, -1>(a, g, max_ctas, stream);
   set_error("conv3x3 tensor-core path: cin=%d x %d sources, cout tile %d does not fit in shared memory", CIN, a.num_src, NT);
   return LV_ERR_INVALID;
 }
@@ -505,11 +441,8 @@ int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream) {
   if (tt == 0) return LV_OK;
   LV_CHECK_ARG(tt < (1ll << 31), "conv3x3: too many tiles (%lld)", tt);
   g.total_tiles = static_cast<int>(tt);
-  TcLaunch L;
-  L.staged = (a.epilogue == LV_EPI_NHWC && g.ntiles_n == 1 && a.cout == g.cout_pad) ? 1 : 0;
-  L.nres = (a.mask != nullptr) + (a.res1 != nullptr) + (a.res2 != nullptr);
 #define LV_TC_CASE(CI, NTV) \
-  if (a.cin == CI && g.nt == NTV) return dispatch_stages<CI, NTV>(a, g, L, max_ctas, stream);
+  if (a.cin == CI && g.nt == NTV) return dispatch_stages<CI, NTV>(a, g, max_ctas, stream);
   LV_TC_CASE(48, 48)
   LV_TC_CASE(48, 96)
   LV_TC_CASE(64, 64)

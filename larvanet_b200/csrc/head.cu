@@ -70,7 +70,6 @@ head_bicubic_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) in[c * 9 + ky * 3 + kx] = sc[c][ty + ky][tx + kx];
-  T* fp = fea + ((static_cast<size_t>(n) * H + gy) * W + gx) * cout;
   for (int co0 = 0; co0 < cout; co0 += 16) {
     float acc[16];
 #pragma unroll
@@ -80,7 +79,7 @@ head_bicubic_kernel(const float* __restrict__ x, const float* __restrict__ w, co
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[i] = fmaf(in[k], sw[k * cout + co0 + i], acc[i]);
     }
-    store16(fp + co0, acc);
+    store16_act(fea, n, gy, gx, co0, H, W, cout, acc);
   }
 
   // ---- bicubic x4 base ----
@@ -189,7 +188,7 @@ head_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* 
     for (int i = t; i < kGH * kGW * cout; i += blockDim.x) {
       const int p = i / cout, co = i - p * cout;
       const int gy = y0 + p / kGW, gx = x0 + p % kGW;
-      sdy[p * cp + co] = (gy < H && gx < W) ? to_f32(dy[((static_cast<size_t>(n) * H + gy) * W + gx) * cout + co]) : 0.f;
+      sdy[p * cp + co] = (gy < H && gx < W) ? to_f32(dy[act_off(n, gy, gx, co >> 3, H, W, cout >> 3) + (co & 7)]) : 0.f;
     }
     __syncthreads();
     if (active) {

@@ -94,23 +94,28 @@ int pack_weights(const lv_pack_item* items, int count, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// NCHW fp32 <-> planar-8 activation layout [N][H][C/8][W][8]; one thread per destination element
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long long HW, long long total) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int H, int W, long long total) {
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
-    const int c = static_cast<int>(i % C);
-    const long long p = i / C;          // n*HW + hw
-    const long long n = p / HW, hw = p % HW;
-    dst[i] = from_f32<T>(src[(n * C + c) * HW + hw]);
+    long long r = i;
+    const int e = static_cast<int>(r % 8); r /= 8;
+    const int x = static_cast<int>(r % W); r /= W;
+    const int ch = static_cast<int>(r % (C / 8)); r /= (C / 8);
+    const int y = static_cast<int>(r % H);
+    const long long n = r / H;
+    dst[i] = from_f32<T>(src[((n * C + ch * 8 + e) * H + y) * W + x]);
   }
 }
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, long long HW, long long total) {
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int H, int W, long long total) {
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
-    const long long hw = i % HW;
-    const long long nc = i / HW;
-    const int c = static_cast<int>(nc % C);
-    const long long n = nc / C;
-    dst[i] = to_f32(src[(n * HW + hw) * C + c]);
+    long long r = i;
+    const int x = static_cast<int>(r % W); r /= W;
+    const int y = static_cast<int>(r % H); r /= H;
+    const int c = static_cast<int>(r % C);
+    const long long n = r / C;
+    dst[i] = to_f32(src[act_off(static_cast<int>(n), y, x, c >> 3, H, W, C >> 3) + (c & 7)]);
   }
 }
 
@@ -123,22 +128,24 @@ static unsigned grid_for(long long total) {
 int nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dtype, cudaStream_t stream) {
   const long long total = static_cast<long long>(n) * c * h * w;
   if (total == 0) return LV_OK;
+  LV_CHECK_ARG(c % 8 == 0, "activation layout needs channels %% 8 == 0 (got %d)", c);
   if (dtype == LV_F32)
-    nchw_to_nhwc_kernel<float><<<grid_for(total), 256, 0, stream>>>(src, static_cast<float*>(dst), c, 1ll * h * w, total);
+    nchw_to_nhwc_kernel<float><<<grid_for(total), 256, 0, stream>>>(src, static_cast<float*>(dst), c, h, w, total);
   else
-    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), c,
-                                                                            1ll * h * w, total);
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), c, h, w,
+                                                                            total);
   LV_LAUNCH_OK();
   return LV_OK;
 }
 int nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int dtype, cudaStream_t stream) {
   const long long total = static_cast<long long>(n) * c * h * w;
   if (total == 0) return LV_OK;
+  LV_CHECK_ARG(c % 8 == 0, "activation layout needs channels %% 8 == 0 (got %d)", c);
   if (dtype == LV_F32)
-    nhwc_to_nchw_kernel<float><<<grid_for(total), 256, 0, stream>>>(static_cast<const float*>(src), dst, c, 1ll * h * w, total);
+    nhwc_to_nchw_kernel<float><<<grid_for(total), 256, 0, stream>>>(static_cast<const float*>(src), dst, c, h, w, total);
   else
     nhwc_to_nchw_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), dst, c,
-                                                                            1ll * h * w, total);
+                                                                            h, w, total);
   LV_LAUNCH_OK();
   return LV_OK;
 }
@@ -169,7 +176,7 @@ l1_loss_grad_kernel(const float* __restrict__ out, const float* __restrict__ tru
         g[4 * r + j] = (d[j] > 0.f) ? 1.f : ((d[j] < 0.f) ? -1.f : 0.f);
       }
     }
-    if (grad_sign != nullptr) store16(grad_sign + ((n * H + y) * W + x) * (16ll * C) + 16 * c, g);
+    if (grad_sign != nullptr) store16_act(grad_sign, static_cast<int>(n), y, x, 16 * c, H, W, 16 * C, g);
   }
   loss = warp_sum(loss);
   if ((threadIdx.x & 31) == 0 && loss_sum != nullptr) atomicAdd(loss_sum, static_cast<double>(loss));

@@ -112,6 +112,46 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float* v) {
   *reinterpret_cast<uint4*>(p) = t;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Activation layout ("planar-8"): [N][H][C/8][W][8] -- for every image row, each 8-channel chunk is a contiguous run
+// of W pixels x 16 B (bf16).  Why not NHWC: (1) a halo-tile row of one chunk is one contiguous 160 B run, so a tile is
+// 108 TMA box rows instead of 1080 16-byte gathers and lands in shared memory already in UMMA operand order;
+// (2) a warp of the epilogue (4 tile rows x 8 pixels, one pixel per thread) reads/writes four full 128 B lines per
+// 8-channel chunk straight from registers -- no shared-memory staging, which matters because shared-memory bandwidth
+// is what bounds the conv kernel.  Element offset of channel chunk `ch8` of pixel (n,y,x):
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t act_off(int n, int y, int x, int ch8, int H, int W, int CH) {
+  return (((static_cast<size_t>(n) * H + y) * CH + ch8) * W + x) * 8;
+}
+// 16 consecutive channels (two chunks) of one pixel
+template <typename T>
+__device__ __forceinline__ void load16_act(const T* base, int n, int y, int x, int co0, int H, int W, int C, float* v) {
+  const size_t o = act_off(n, y, x, co0 >> 3, H, W, C >> 3);
+  if constexpr (sizeof(T) == 2) {
+    load8(base + o, v);
+    load8(base + o + static_cast<size_t>(W) * 8, v + 8);
+  } else {
+    const float4* p0 = reinterpret_cast<const float4*>(base + o);
+    const float4* p1 = reinterpret_cast<const float4*>(base + o + static_cast<size_t>(W) * 8);
+    const float4 a = p0[0], b = p0[1], c = p1[0], d = p1[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store16_act(T* base, int n, int y, int x, int co0, int H, int W, int C, const float* v) {
+  const size_t o = act_off(n, y, x, co0 >> 3, H, W, C >> 3);
+  if constexpr (sizeof(T) == 2) {
+    store8(base + o, v);
+    store8(base + o + static_cast<size_t>(W) * 8, v + 8);
+  } else {
+    float4* p0 = reinterpret_cast<float4*>(base + o);
+    float4* p1 = reinterpret_cast<float4*>(base + o + static_cast<size_t>(W) * 8);
+    p0[0] = make_float4(v[0], v[1], v[2], v[3]); p0[1] = make_float4(v[4], v[5], v[6], v[7]);
+    p1[0] = make_float4(v[8], v[9], v[10], v[11]); p1[1] = make_float4(v[12], v[13], v[14], v[15]);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -187,8 +227,12 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_hint(bar, parity, 400u)) {
+    __nanosleep(128);   // back off: eight spinning epilogue warps otherwise issue a third of the SM's instructions
     if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
   }
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // ---- proxy / tcgen05 fences ----

@@ -82,14 +82,14 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
       if (idx < n_dy) {
         const int p = idx / cho, c = idx - p * cho;
         pc_dst[i] = c * kDyPlane + p * 16;
-        pc_rel[i] = ((p >> 3) * it.w + (p & 7)) * it.cout + c * 8;
+        pc_rel[i] = (((p >> 3) * cho + c) * it.w + (p & 7)) * 8;
         pc_rc[i] = ((p >> 3) << 8) | (p & 7);                       // bit 30 clear: dY piece (tile coordinates)
       } else if (idx < n_all) {
         const int j = idx - n_dy;
         const int p = j / (kWCin / 8), c = j - p * (kWCin / 8);
         const int r = p / kWHaloW, col = p - r * kWHaloW;
         pc_dst[i] = kDyBytes + c * kXPlane + p * 16;
-        pc_rel[i] = ((r - 1) * it.w + (col - 1)) * kWCin + c * 8;
+        pc_rel[i] = (((r - 1) * (kWCin / 8) + c) * it.w + (col - 1)) * 8;
         pc_rc[i] = (1 << 30) | (r << 8) | col;                      // bit 30 set: X halo piece (halo coordinates)
       } else {
         pc_dst[i] = 0; pc_rel[i] = 0; pc_rc[i] = -1;
@@ -103,9 +103,9 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
       const int stage = fill % kWStages;
       mbar_wait_relaxed(empty_bar(stage), ((fill / kWStages) & 1) ^ 1);
       const uint32_t st0 = smem_u32(smem + stage * kWStageBytes);
-      const long long org = (static_cast<long long>(n) * it.h + y0) * it.w + x0;
-      const __nv_bfloat16* dy_org = DY + org * it.cout;
-      const __nv_bfloat16* x_org = X + org * kWCin;
+      // planar-8 layout: element offset of (n, y0, chunk 0, x0)
+      const __nv_bfloat16* dy_org = DY + ((static_cast<long long>(n) * it.h + y0) * cho * it.w + x0) * 8;
+      const __nv_bfloat16* x_org = X + ((static_cast<long long>(n) * it.h + y0) * (kWCin / 8) * it.w + x0) * 8;
 #pragma unroll
       for (int i = 0; i < kMaxPieces; ++i) {
         if (pc_rc[i] >= 0) {
@@ -246,14 +246,14 @@ wgrad_simt_kernel(const lv_wgrad_item* __restrict__ items, int splits) {
         const int hp = idx / cin, ci = idx % cin;
         const int gy = y0 - 1 + hp / kSWHaloW, gx = x0 - 1 + hp % kSWHaloW;
         float v = 0.f;
-        if (gy >= 0 && gy < it.h && gx >= 0 && gx < it.w) v = to_f32(X[((static_cast<size_t>(n) * it.h + gy) * it.w + gx) * cin + ci]);
+        if (gy >= 0 && gy < it.h && gx >= 0 && gx < it.w) v = to_f32(X[act_off(n, gy, gx, ci >> 3, it.h, it.w, cin >> 3) + (ci & 7)]);
         sx[hp * cinp + ci] = v;
       }
       for (int idx = threadIdx.x; idx < 128 * cout; idx += 256) {
         const int p = idx / cout, co = idx % cout;
         const int gy = y0 + p / kSW_W, gx = x0 + p % kSW_W;
         float v = 0.f;
-        if (gy < it.h && gx < it.w) v = to_f32(DY[((static_cast<size_t>(n) * it.h + gy) * it.w + gx) * cout + co]);
+        if (gy < it.h && gx < it.w) v = to_f32(DY[act_off(n, gy, gx, co >> 3, it.h, it.w, cout >> 3) + (co & 7)]);
         sdy[p * cop + co] = v;
       }
       __syncthreads();
@@ -296,7 +296,8 @@ static int check_items(const lv_wgrad_item* items, int count) {
     const lv_wgrad_item& a = items[k];
     LV_CHECK_ARG(a.x && a.dy && a.dw, "wgrad: null pointer in item %d", k);
     LV_CHECK_ARG(a.dtype == items[0].dtype, "wgrad: mixed dtypes in one batch");
-    LV_CHECK_ARG(a.cin > 0 && a.cout > 0 && a.cin <= 64 && a.cout <= 64, "wgrad: cin/cout must be in 1..64 (item %d)", k);
+    LV_CHECK_ARG(a.cin > 0 && a.cout > 0 && a.cin <= 64 && a.cout <= 64 && a.cin % 8 == 0 && a.cout % 8 == 0,
+                 "wgrad: cin/cout must be multiples of 8 in 8..64 (item %d)", k);
     LV_CHECK_ARG(a.cin_off >= 0 && a.cin_off + a.cin <= a.cin_total, "wgrad: bad cin slice (item %d)", k);
   }
   return LV_OK;

@@ -11,7 +11,7 @@ models/LarvaNetV2.py:101-123, :355-365) becomes:
             straight into a flat fp32 gradient arena, so zero_grad is one memset, the data-parallel exchange is one
             allreduce per body slice and AdamW is one kernel.
 
-Activations are NHWC in `act_dtype` (bf16 = product path on tcgen05 tensor cores, fp32 = validation mode).
+Activations are planar-8 ([n][h][c/8][w][8], see csrc/lv_common.cuh) in `act_dtype` (bf16 = product path on tcgen05 tensor cores, fp32 = validation mode).
 Everything here is plumbing: tensors, streams, graphs.  No arithmetic happens in PyTorch.
 """
 from __future__ import annotations
@@ -75,6 +75,29 @@ class ParamArena:
 
 class _Bufs:
     pass
+
+
+def _capture_graph(run):
+    """Warm up `run()` eagerly, then capture it into a CUDA graph.  Returns (graph, launches) or (None, 0) when the
+    capture was invalidated (seen once after unrelated allocator churn); the caller then keeps launching the same CUDA
+    kernels eagerly -- slower to launch, numerically identical, never a different code path."""
+    import gc
+    import warnings
+    run()  # warm-up: module loading, cudaFuncSetAttribute, allocator growth all happen outside the capture
+    torch.cuda.current_stream().synchronize()
+    for attempt in range(2):
+        gc.collect()
+        g = torch.cuda.CUDAGraph()
+        c0 = _lib.launch_count()
+        try:
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
+                run()
+            return g, _lib.launch_count() - c0
+        except Exception as e:  # noqa: BLE001
+            torch.cuda.synchronize()
+            err = e
+    warnings.warn(f'larvanet_b200: CUDA graph capture failed twice ({type(err).__name__}: {err}); running eagerly')
+    return None, 0
 
 
 class LarvaEngine:
@@ -170,7 +193,7 @@ class LarvaEngine:
                     **kw)
 
     def _act(self, n, h, w, c=C):
-        return torch.empty((n, h, w, c), dtype=self.act_dtype, device=self.device)
+        return ops.act_empty(n, h, w, c, self.act_dtype, self.device)
 
     # ------------------------------------------------------------------ inference
     def _build_infer(self, n, h, w, exit_leg=None):
@@ -233,16 +256,14 @@ class LarvaEngine:
             return b.out
         if self.use_graphs and not self.simt:
             if ent[1] is None:
-                self._run_infer(b, exit_leg)  # warm-up (also sets func attributes outside capture)
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                c0 = _lib.launch_count()
-                with torch.cuda.graph(g):
-                    self._run_infer(b, exit_leg)
-                ent[1] = g
-                ent.append(_lib.launch_count() - c0)
-            ent[1].replay()
-            self.replayed_launches += ent[2]
+                g, nl = _capture_graph(lambda: self._run_infer(b, exit_leg))
+                ent[1] = g if g is not None else False
+                ent.append(nl)
+            if ent[1]:
+                ent[1].replay()
+                self.replayed_launches += ent[2]
+            else:
+                self._run_infer(b, exit_leg)
         else:
             self._run_infer(b, exit_leg)
         return b.out
@@ -393,16 +414,14 @@ class LarvaEngine:
         self.arena.attach_grads()
         if self.use_graphs and not self.simt:
             if ent[1] is None:
+                g, nl = _capture_graph(lambda: self._run_train(b))
+                ent[1] = g if g is not None else False
+                ent.append(nl)
+            if ent[1]:
+                ent[1].replay()
+                self.replayed_launches += ent[2]
+            else:
                 self._run_train(b)
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                c0 = _lib.launch_count()
-                with torch.cuda.graph(g):
-                    self._run_train(b)
-                ent[1] = g
-                ent.append(_lib.launch_count() - c0)
-            ent[1].replay()
-            self.replayed_launches += ent[2]
         else:
             self._run_train(b)
         if self.world_size > 1:
@@ -420,8 +439,9 @@ class LarvaEngine:
         like oracle.larva_oracle.larvanet_train_step(tapes_from=...).  For parity tests / debugging only."""
         b = self._last_train
 
-        def cv(a):
-            return a.detach().to(torch.float32).permute(0, 3, 1, 2).contiguous().cpu().numpy()
+        def cv(a):   # planar-8 [n,h,c/8,w,8] -> NCHW
+            n, h, ch, w, _ = a.shape
+            return a.detach().to(torch.float32).permute(0, 2, 4, 1, 3).reshape(n, ch * 8, h, w).contiguous().cpu().numpy()
 
         t = {'f0': cv(b.f0)}
         for i, nb in enumerate(self.blocks):
@@ -442,12 +462,12 @@ class LarvaEngine:
     def _to_act(self, x_nchw):
         x = x_nchw.detach().to(device=self.device, dtype=torch.float32).contiguous()
         n, c, h, w = (int(v) for v in x.shape)
-        a = torch.empty((n, h, w, c), dtype=self.act_dtype, device=self.device)
+        a = ops.act_empty(n, h, w, c, self.act_dtype, self.device)
         ops.nchw_to_nhwc(x, a)
         return a
 
     def _to_nchw(self, a):
-        n, h, w, c = (int(v) for v in a.shape)
+        n, h, w, c = ops.act_dims(a)
         y = torch.empty((n, c, h, w), dtype=torch.float32, device=self.device)
         ops.nhwc_to_nchw(a, y)
         return y
@@ -469,7 +489,7 @@ class LarvaEngine:
         return out
 
     def _resblock(self, i, j, a, fin=None):
-        n, h, w, _ = (int(v) for v in a.shape)
+        n, h, w, _ = ops.act_dims(a)
         p = f'body_{i}.res_blocks.{j}.body'
         t, o = self._act(n, h, w), self._act(n, h, w)
         self._conv([a], p + '.0', out=t, relu=True)
@@ -490,7 +510,7 @@ class LarvaEngine:
         return self._to_nchw(a)
 
     def _recon(self, prefix, fea, base):
-        n, h, w, _ = (int(v) for v in fea.shape)
+        n, h, w, _ = ops.act_dims(fea)
         base = base.detach().to(device=self.device, dtype=torch.float32).contiguous()
         u = self._act(n, h, w)
         out = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=self.device)
@@ -505,7 +525,7 @@ class LarvaEngine:
     def run_tail(self, features, base):
         self.repack()
         feats = [self._to_act(f) for f in features]
-        n, h, w, _ = (int(v) for v in feats[0].shape)
+        n, h, w, _ = ops.act_dims(feats[0])
         mf = self._act(n, h, w)
         self._conv(feats, 'tail.merge_conv', out=mf)
         return self._recon('tail', mf, base)
@@ -572,10 +592,10 @@ class EdsrEngine:
         b = _Bufs()
         dev, dt, f = self.device, self.act_dtype, self.f
         b.x = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
-        b.x0 = torch.empty((n, h, w, f), dtype=dt, device=dev)
+        b.x0 = ops.act_empty(n, h, w, f, dt, dev)
         b.t = torch.empty_like(b.x0)
         b.pp = [torch.empty_like(b.x0), torch.empty_like(b.x0)]
-        b.up = [torch.empty((n, h << (s + 1), w << (s + 1), f), dtype=dt, device=dev) for s in range(self.nup)]
+        b.up = [ops.act_empty(n, h << (s + 1), w << (s + 1), f, dt, dev) for s in range(self.nup)]
         b.out = torch.empty((n, 3, h * self.scale, w * self.scale), dtype=torch.float32, device=dev)
         return b
 
@@ -616,16 +636,14 @@ class EdsrEngine:
             return b.out
         if self.use_graphs and not self.simt:
             if ent[1] is None:
+                g, nl = _capture_graph(lambda: self._run(b))
+                ent[1] = g if g is not None else False
+                ent.append(nl)
+            if ent[1]:
+                ent[1].replay()
+                self.replayed_launches += ent[2]
+            else:
                 self._run(b)
-                torch.cuda.current_stream().synchronize()
-                g = torch.cuda.CUDAGraph()
-                c0 = _lib.launch_count()
-                with torch.cuda.graph(g):
-                    self._run(b)
-                ent[1] = g
-                ent.append(_lib.launch_count() - c0)
-            ent[1].replay()
-            self.replayed_launches += ent[2]
         else:
             self._run(b)
         return b.out

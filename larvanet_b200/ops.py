@@ -1,5 +1,7 @@
 """Tensor-level wrappers over the C-ABI: validate torch tensors, pass raw device pointers + the current stream.
 
+Activation tensors use the library's planar-8 layout and have torch shape [n, h, c/8, w, 8] (see `act_empty`).
+
 PyTorch is only the owner of device memory and streams here; every function ends in exactly one `lv_*` call.
 No function in this file has a fallback path.
 """
@@ -39,6 +41,21 @@ def _ptr(t, dtype=None, name='tensor'):
     return t.data_ptr()
 
 
+def act_empty(n, h, w, c, dtype, device):
+    """Allocate an activation tensor in the library's planar-8 layout [n][h][c/8][w][8]."""
+    if c % 8 != 0:
+        raise _lib.LarvaNetB200Error(f'activation tensors need channels % 8 == 0 (got {c})')
+    return torch.empty((n, h, c // 8, w, 8), dtype=dtype, device=device)
+
+
+def act_dims(t):
+    """(n, h, w, c) of a planar-8 activation tensor."""
+    if t.dim() != 5 or t.shape[4] != 8:
+        raise _lib.LarvaNetB200Error(f'expected a planar-8 activation tensor [n,h,c/8,w,8], got shape {tuple(t.shape)}')
+    n, h, ch, w, _ = (int(v) for v in t.shape)
+    return n, h, w, ch * 8
+
+
 def device_check(device_index=None):
     lib = _lib.load()
     dev = torch.cuda.current_device() if device_index is None else device_index
@@ -75,10 +92,10 @@ def pack_weights(items):
 def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res1=None, res2=None, out=None,
                    epilogue=LV_EPI_NHWC, out_hr=None, base_hr=None, truth_hr=None, loss_sum=None, grad_sign=None,
                    post_w=None, post_b=None, res_scale=1.0):
-    """Build an lv_conv_args from torch tensors.  srcs: list of NHWC [n,h,w,cin] tensors (same shape/dtype)."""
+    """Build an lv_conv_args from torch tensors.  srcs: list of planar-8 activation tensors (same shape/dtype)."""
     x0 = srcs[0]
     dt = x0.dtype
-    n, h, w, cin = (int(v) for v in x0.shape)
+    n, h, w, cin = act_dims(x0)
     a = ConvArgs()
     a.n, a.h, a.w, a.cin, a.num_src, a.cout = n, h, w, cin, len(srcs), int(cout)
     a.dtype = dtype_id(dt)
@@ -149,7 +166,7 @@ def bicubic_x4(x, out):
 
 def head_wgrad(x, dy, dw, db, scale):
     n, c, h, w = (int(v) for v in x.shape)
-    cout = int(dy.shape[3])
+    cout = act_dims(dy)[3]
     check(_lib.load().lv_head_wgrad(_ptr(x, torch.float32, 'x'), _ptr(dy, None, 'dy'), _ptr(dw, torch.float32, 'dw'),
                                     _ptr(db, torch.float32, 'db'), n, h, w, cout, dtype_id(dy.dtype), float(scale),
                                     _stream()), 'lv_head_wgrad')
@@ -166,9 +183,9 @@ class WgradBatch:
         self._keep = []
         for k, it in enumerate(items):
             x, dy, dw, db = it['x'], it['dy'], it['dw'], it.get('db')
-            n, h, w, cin = (int(v) for v in x.shape)
+            n, h, w, cin = act_dims(x)
             hi = self.host[k]
-            hi.n, hi.h, hi.w, hi.cin, hi.cout = n, h, w, cin, int(dy.shape[3])
+            hi.n, hi.h, hi.w, hi.cin, hi.cout = n, h, w, cin, act_dims(dy)[3]
             hi.cin_total = int(it.get('cin_total', cin))
             hi.cin_off = int(it.get('cin_off', 0))
             hi.dtype = dtype_id(x.dtype)
@@ -204,7 +221,7 @@ def nchw_to_nhwc(src, dst):
 
 
 def nhwc_to_nchw(src, dst):
-    n, h, w, c = (int(v) for v in src.shape)
+    n, h, w, c = act_dims(src)
     check(_lib.load().lv_nhwc_to_nchw(_ptr(src, None, 'src'), _ptr(dst, torch.float32, 'dst'), n, c, h, w,
                                       dtype_id(src.dtype), _stream()), 'lv_nhwc_to_nchw')
 

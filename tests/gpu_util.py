@@ -12,11 +12,21 @@ def bf16_round(a):
 
 
 def to_nhwc(x_nchw, dtype, device='cuda'):
-    return torch.from_numpy(np.ascontiguousarray(x_nchw.transpose(0, 2, 3, 1), dtype=np.float32)).to(device).to(dtype).contiguous()
+    """NCHW numpy -> the library's planar-8 activation layout [n][h][c/8][w][8] (name kept from the NHWC days)."""
+    n, c, h, w = x_nchw.shape
+    a = np.ascontiguousarray(x_nchw.reshape(n, c // 8, 8, h, w).transpose(0, 3, 1, 4, 2), dtype=np.float32)
+    return torch.from_numpy(a).to(device).to(dtype).contiguous()
 
 
 def from_nhwc(t):
-    return t.detach().to(torch.float32).cpu().numpy().transpose(0, 3, 1, 2).astype(np.float64)
+    """planar-8 activation tensor -> NCHW float64 numpy."""
+    n, h, ch, w, _ = t.shape
+    a = t.detach().to(torch.float32).cpu().numpy()
+    return a.transpose(0, 2, 4, 1, 3).reshape(n, ch * 8, h, w).astype(np.float64)
+
+
+def act_empty(n, h, w, c, dtype, device='cuda'):
+    return torch.empty((n, h, c // 8, w, 8), dtype=dtype, device=device)
 
 
 def rel_l2(a, b):

@@ -10,7 +10,7 @@ import torch
 
 from larvanet_b200 import _lib, ops
 from oracle import larva_oracle as O
-from tests.gpu_util import bf16_round, from_nhwc, rel_l2, to_nhwc
+from tests.gpu_util import act_empty, bf16_round, from_nhwc, rel_l2, to_nhwc
 
 pytestmark = pytest.mark.gpu
 
@@ -159,7 +159,7 @@ def test_head_and_bicubic(prec):
     x = rs.uniform(0, 255, (n, 3, h, w)).astype(np.float32)
     wt = (rs.standard_normal((48, 3, 3, 3)) * 0.05).astype(np.float32)
     b = (rs.standard_normal(48) * 0.5).astype(np.float32)
-    fea = torch.empty((n, h, w, 48), dtype=dtype, device='cuda')
+    fea = act_empty(n, h, w, 48, dtype)
     base = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device='cuda')
     ops.head_bicubic(torch.from_numpy(x).cuda(), torch.from_numpy(wt).cuda(), torch.from_numpy(b).cuda(), fea, base)
     ref = O.conv2d(x.astype(np.float64), wt.astype(np.float64), b.astype(np.float64))
@@ -220,7 +220,7 @@ def test_layout_loss_adamw_helpers():
     rs = np.random.RandomState(31)
     x = rs.standard_normal((2, 48, 7, 5)).astype(np.float32)
     for dtype in (torch.float32, torch.bfloat16):
-        a = torch.empty((2, 7, 5, 48), dtype=dtype, device='cuda')
+        a = act_empty(2, 7, 5, 48, dtype)
         ops.nchw_to_nhwc(torch.from_numpy(x).cuda(), a)
         back = torch.empty((2, 48, 7, 5), dtype=torch.float32, device='cuda')
         ops.nhwc_to_nchw(a, back)
@@ -230,7 +230,7 @@ def test_layout_loss_adamw_helpers():
     truth = rs.uniform(0, 255, (2, 3, 16, 12)).astype(np.float32)
     truth[0, 0, 0, 0] = out[0, 0, 0, 0]  # sign(0) == 0
     loss = torch.zeros(1, dtype=torch.float64, device='cuda')
-    g = torch.empty((2, 4, 3, 48), dtype=torch.bfloat16, device='cuda')
+    g = act_empty(2, 4, 3, 48, torch.bfloat16)
     ops.l1_loss_grad(torch.from_numpy(out).cuda(), torch.from_numpy(truth).cuda(), loss, g)
     assert abs(loss.item() - np.abs(out.astype(np.float64) - truth).sum()) < 1e-3
     np.testing.assert_array_equal(from_nhwc(g), O.pixel_unshuffle(np.sign(out.astype(np.float64) - truth), 4))
@@ -248,8 +248,11 @@ def test_layout_loss_adamw_helpers():
 
 
 def test_errors_are_loud():
-    x = torch.zeros((1, 8, 8, 40), dtype=torch.bfloat16, device='cuda')
+    x = torch.zeros((1, 8, 5, 8, 8), dtype=torch.bfloat16, device='cuda')   # 40 channels: not a multiple of 16
     with pytest.raises(_lib.LarvaNetB200Error):
-        ops.conv3x3([x], torch.zeros(16, dtype=torch.uint8, device='cuda'), 48, out=torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device='cuda'))
+        ops.conv3x3([x], torch.zeros(16, dtype=torch.uint8, device='cuda'), 48, out=act_empty(1, 8, 8, 48, torch.bfloat16))
+    with pytest.raises(_lib.LarvaNetB200Error):   # NHWC-shaped tensors are rejected: the library's layout is planar-8
+        ops.conv3x3([torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device='cuda')], torch.zeros(16, dtype=torch.uint8, device='cuda'), 48,
+                    out=act_empty(1, 8, 8, 48, torch.bfloat16))
     with pytest.raises(_lib.LarvaNetB200Error):
         ops.conv3x3([x.cpu()], torch.zeros(16, dtype=torch.uint8), 48, out=x.cpu())

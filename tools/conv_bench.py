@@ -20,7 +20,7 @@ def main():
     ap.add_argument('--splits', type=int, default=296)
     a = ap.parse_args()
     g = torch.Generator(device='cuda').manual_seed(3)
-    x = torch.randn((a.n, a.h, a.w, 48), device='cuda', generator=g).to(torch.bfloat16)
+    x = torch.randn((a.n, a.h, 6, a.w, 8), device='cuda', generator=g).to(torch.bfloat16)
     wt = torch.randn((48, 48, 3, 3), device='cuda', generator=g) * 0.05
     b = torch.zeros(48, device='cuda')
     packed = torch.zeros(ops.packed_weight_bytes(48, 48, torch.bfloat16), dtype=torch.uint8, device='cuda')

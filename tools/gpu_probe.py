@@ -26,12 +26,10 @@ def pack(w, dtype, cin, **kw):
     return packed
 
 
-def nhwc(x):
-    return x.permute(0, 2, 3, 1).contiguous()
-
-
 def nchw(x):
-    return x.permute(0, 3, 1, 2).contiguous()
+    """planar-8 activation [n,h,c/8,w,8] -> NCHW"""
+    n, h, ch, w, _ = x.shape
+    return x.permute(0, 2, 4, 1, 3).reshape(n, ch * 8, h, w).contiguous()
 
 
 def run(fn, what):
@@ -48,12 +46,12 @@ def conv_check(n, h, w, cin=48, cout=48, nsrc=1, seed=0):
     g = torch.Generator(device='cuda').manual_seed(seed)
     wt = torch.randn((cout, cin * nsrc, 3, 3), device='cuda', generator=g) * 0.05
     b = torch.randn(cout, device='cuda', generator=g)
-    xs = [torch.randn((n, h, w, cin), device='cuda', generator=g).to(torch.bfloat16) for _ in range(nsrc)]
+    xs = [torch.randn((n, h, cin // 8, w, 8), device='cuda', generator=g).to(torch.bfloat16) for _ in range(nsrc)]
     packed = pack(wt, torch.bfloat16, cin)
-    o_tc = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device='cuda')
+    o_tc = torch.empty((n, h, cout // 8, w, 8), dtype=torch.bfloat16, device='cuda')
     o_si = torch.empty_like(o_tc)
     ok = run(lambda: ops.conv3x3(xs, packed, cout, bias=b, out=o_si, simt=True), 'simt')
-    ref = F.conv2d(nchw(torch.cat(xs, 3).float()), wt.to(torch.bfloat16).float(), b, padding=1)
+    ref = F.conv2d(torch.cat([nchw(x.float()) for x in xs], 1), wt.to(torch.bfloat16).float(), b, padding=1)
     e_si = (nchw(o_si.float()) - ref).abs().max().item()
     ok2 = run(lambda: ops.conv3x3(xs, packed, cout, bias=b, out=o_tc), 'tc')
     e_tc = (nchw(o_tc.float()) - ref).abs().max().item() if ok2 else float('nan')
@@ -66,7 +64,7 @@ def conv_pattern():
     """weights non-zero for a single (tap, 16-channel K step): a 9x3 table of max errors."""
     n, h, w = 1, 16, 8
     g = torch.Generator(device='cuda').manual_seed(1)
-    x = torch.randn((n, h, w, 48), device='cuda', generator=g).to(torch.bfloat16)
+    x = torch.randn((n, h, 6, w, 8), device='cuda', generator=g).to(torch.bfloat16)
     full = torch.randn((48, 48, 3, 3), device='cuda', generator=g) * 0.1
     print('per (tap, kstep) max error of the tensor-core conv (rows: tap 0..8, cols: channels 0-15,16-31,32-47)')
     for tap in range(9):
@@ -75,7 +73,7 @@ def conv_pattern():
             wt = torch.zeros_like(full)
             wt[:, 16 * ks:16 * ks + 16, tap // 3, tap % 3] = full[:, 16 * ks:16 * ks + 16, tap // 3, tap % 3]
             packed = pack(wt, torch.bfloat16, 48)
-            o = torch.empty((n, h, w, 48), dtype=torch.bfloat16, device='cuda')
+            o = torch.empty((n, h, 6, w, 8), dtype=torch.bfloat16, device='cuda')
             if not run(lambda: ops.conv3x3([x], packed, 48, out=o), f'pattern tap{tap} ks{ks}'):
                 return
             ref = F.conv2d(nchw(x.float()), wt.to(torch.bfloat16).float(), None, padding=1)
@@ -85,8 +83,8 @@ def conv_pattern():
 
 def wgrad_check(n, h, w, splits):
     g = torch.Generator(device='cuda').manual_seed(2)
-    x = torch.randn((n, h, w, 48), device='cuda', generator=g).to(torch.bfloat16)
-    dy = torch.randn((n, h, w, 48), device='cuda', generator=g).to(torch.bfloat16)
+    x = torch.randn((n, h, 6, w, 8), device='cuda', generator=g).to(torch.bfloat16)
+    dy = torch.randn((n, h, 6, w, 8), device='cuda', generator=g).to(torch.bfloat16)
     res = {}
     for simt in (True, False):
         dw = torch.zeros((48, 48, 3, 3), device='cuda')
@@ -129,7 +127,7 @@ def timeit(fn, iters=20, warm=3):
 def conv_timing():
     for (n, h, w) in [(1, 180, 320), (16, 48, 48), (1, 270, 480), (32, 270, 480)]:
         g = torch.Generator(device='cuda').manual_seed(3)
-        x = torch.randn((n, h, w, 48), device='cuda', generator=g).to(torch.bfloat16)
+        x = torch.randn((n, h, 6, w, 8), device='cuda', generator=g).to(torch.bfloat16)
         wt = torch.randn((48, 48, 3, 3), device='cuda', generator=g) * 0.05
         b = torch.zeros(48, device='cuda')
         packed = pack(wt, torch.bfloat16, 48)

@@ -11,7 +11,7 @@ def main():
     lib = _lib.load()
     lib.lv_debug_set_timeline.argtypes = [ctypes.c_void_p]
     g = torch.Generator(device='cuda').manual_seed(3)
-    x = torch.randn((n, h, w, 48), device='cuda', generator=g).to(torch.bfloat16)
+    x = torch.randn((n, h, 6, w, 8), device='cuda', generator=g).to(torch.bfloat16)
     wt = torch.randn((48, 48, 3, 3), device='cuda', generator=g) * 0.05
     b = torch.zeros(48, device='cuda')
     packed = torch.zeros(ops.packed_weight_bytes(48, 48, torch.bfloat16), dtype=torch.uint8, device='cuda')
