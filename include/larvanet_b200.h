@@ -43,6 +43,10 @@ enum {
   LV_EPI_RGB_NCHW = 3   /* out_hr[n,c,h,w] = post_w[c,:].v[0:3] + post_b[c]   (EDSR final_conv + 1x1)      */
 };
 
+/* packed weight layouts (LV_BF16): tap-major [ntile][src][tap][cin/8][cout][8] (27 MMAs of N=cout per tile) or
+ * ky-stacked [src][kx][cin/8][ky*cout_pad+cout][8] (9 MMAs of N=3*cout per tile; cout_pad <= 80, one N tile) */
+enum { LV_W_TAP_MAJOR = 0, LV_W_KY_STACKED = 1 };
+
 #define LV_MAX_SRC 4
 
 /*
@@ -63,7 +67,7 @@ typedef struct lv_conv_args {
   int32_t dtype;             /* LV_BF16 | LV_F32 : type of src/out/res/mask/grad_sign                     */
   int32_t relu;
   int32_t epilogue;          /* LV_EPI_*                                                                  */
-  int32_t reserved0;
+  int32_t wlayout;           /* LV_W_TAP_MAJOR | LV_W_KY_STACKED: which packed-weight layout `weights` uses  */
   float res_scale;           /* 1.0 unless EDSR --edsr_res_weight                                        */
   float reserved1;
   const void* src[LV_MAX_SRC]; /* NHWC [n,h,w,cin]                                                        */
@@ -111,7 +115,7 @@ typedef struct lv_pack_item {
   int32_t i_off, i_cnt;
   int32_t cin;
   int32_t dtype;
-  int32_t reserved;
+  int32_t wlayout;           /* LV_W_TAP_MAJOR | LV_W_KY_STACKED (bf16 only)                                          */
 } lv_pack_item;
 
 const char* lv_last_error(void);

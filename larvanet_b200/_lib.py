@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, 'liblarvanet_b200.so')
 LV_F32, LV_BF16 = 0, 1
 LV_EPI_NHWC, LV_EPI_PS4_NCHW, LV_EPI_PS2_NHWC, LV_EPI_RGB_NCHW = 0, 1, 2, 3
 LV_MAX_SRC = 4
+LV_W_TAP_MAJOR, LV_W_KY_STACKED = 0, 1
 ABI_VERSION = 1
 
 
@@ -26,7 +27,7 @@ class ConvArgs(C.Structure):
     _fields_ = [
         ('n', C.c_int32), ('h', C.c_int32), ('w', C.c_int32),
         ('cin', C.c_int32), ('num_src', C.c_int32), ('cout', C.c_int32),
-        ('dtype', C.c_int32), ('relu', C.c_int32), ('epilogue', C.c_int32), ('reserved0', C.c_int32),
+        ('dtype', C.c_int32), ('relu', C.c_int32), ('epilogue', C.c_int32), ('wlayout', C.c_int32),
         ('res_scale', C.c_float), ('reserved1', C.c_float),
         ('src', C.c_void_p * LV_MAX_SRC),
         ('weights', C.c_void_p), ('bias', C.c_void_p), ('mask', C.c_void_p),
@@ -52,7 +53,7 @@ class PackItem(C.Structure):
         ('w', C.c_void_p), ('packed', C.c_void_p),
         ('O', C.c_int32), ('I', C.c_int32), ('transpose', C.c_int32),
         ('i_off', C.c_int32), ('i_cnt', C.c_int32), ('cin', C.c_int32),
-        ('dtype', C.c_int32), ('reserved', C.c_int32),
+        ('dtype', C.c_int32), ('wlayout', C.c_int32),
     ]
 
 

@@ -35,6 +35,7 @@ int sm_count() {
 
 // implemented in the other translation units
 int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
+int conv3x3_tc_ky(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
 int conv3x3_simt(const lv_conv_args& a, cudaStream_t stream);
 int pick_ntile(int cout_pad);
 extern long long* g_timeline;
@@ -59,6 +60,7 @@ static int check_conv(const lv_conv_args* a) {
   LV_CHECK_ARG(a->num_src >= 1 && a->num_src <= LV_MAX_SRC, "conv3x3: num_src must be 1..%d", LV_MAX_SRC);
   LV_CHECK_ARG(a->cin > 0 && a->cout > 0, "conv3x3: bad channel counts");
   LV_CHECK_ARG(a->weights != nullptr, "conv3x3: null weights");
+  LV_CHECK_ARG(a->wlayout == LV_W_TAP_MAJOR || (a->wlayout == LV_W_KY_STACKED && a->dtype == LV_BF16), "conv3x3: bad wlayout %d", a->wlayout);
   for (int s = 0; s < a->num_src; ++s) LV_CHECK_ARG(a->src[s] != nullptr, "conv3x3: null source %d", s);
   switch (a->epilogue) {
     case LV_EPI_NHWC:
@@ -128,6 +130,7 @@ int lv_conv3x3(const lv_conv_args* a, int max_ctas, void* stream) {
   if (rc != LV_OK) return rc;
   if (a->dtype == LV_BF16) {
     LV_CHECK_ARG(a->cin % 16 == 0, "conv3x3: the tensor-core path needs cin %% 16 == 0 (got %d)", a->cin);
+    if (a->wlayout == LV_W_KY_STACKED) return conv3x3_tc_ky(*a, max_ctas, static_cast<cudaStream_t>(stream));
     return conv3x3_tc(*a, max_ctas, static_cast<cudaStream_t>(stream));
   }
   return conv3x3_simt(*a, static_cast<cudaStream_t>(stream));

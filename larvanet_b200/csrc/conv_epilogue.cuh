@@ -25,7 +25,7 @@ __device__ __forceinline__ void tl_stamp(const ConvGeom& g, int role, uint32_t t
   if (g.timeline != nullptr && blockIdx.x == 0 && tile_k < 64) g.timeline[(role * 64 + tile_k) * 4 + ev] = clock64();
 }
 
-template <typename T>
+template <typename T, bool ADD_BIAS = true>
 __device__ __forceinline__ float conv_epilogue16(const lv_conv_args& a, int n, int y, int x, int co0, float* v) {
   const int H = a.h, W = a.w, C = a.cout;
   // 1. bias + scale
@@ -33,7 +33,7 @@ __device__ __forceinline__ float conv_epilogue16(const lv_conv_args& a, int n, i
   for (int i = 0; i < 16; ++i) {
     const int co = co0 + i;
     float b = 0.f;
-    if (a.bias != nullptr && co < C) b = __ldg(a.bias + co);
+    if (ADD_BIAS && a.bias != nullptr && co < C) b = __ldg(a.bias + co);
     v[i] = (co < C) ? a.res_scale * (v[i] + b) : 0.f;
   }
   // 2. ReLU

@@ -72,15 +72,24 @@ conv3x3_simt_kernel(const __grid_constant__ lv_conv_args a, int tiles_x, int til
           } else {
             // tensor-core operand layout: [ntile][src][tap][chunk][co_in_tile][8] bf16
             const int ntile = co0 / nt, co_in = co0 % nt, ch = cin / 8;
-            const uint4* wp = reinterpret_cast<const uint4*>(a.weights) +
-                              ((static_cast<size_t>(ntile) * a.num_src + s) * 9 + tap) * ch * nt + co_in;
+            const uint4* wp;
+            size_t wstride;   // uint4 units between consecutive 8-channel chunks
+            if (a.wlayout == LV_W_KY_STACKED) {  // [src][kx][chunk][ky*cout_pad + co][8]
+              wp = reinterpret_cast<const uint4*>(a.weights) +
+                   (static_cast<size_t>(s * 3 + tap % 3) * ch) * (3 * cout_pad) + (tap / 3) * cout_pad + co0;
+              wstride = 3 * cout_pad;
+            } else {
+              wp = reinterpret_cast<const uint4*>(a.weights) +
+                   ((static_cast<size_t>(ntile) * a.num_src + s) * 9 + tap) * ch * nt + co_in;
+              wstride = nt;
+            }
             for (int c8 = 0; c8 < ch; ++c8) {
               float xv[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) xv[e] = xp[c8 * 8 + e];
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const uint4 w = __ldg(wp + static_cast<size_t>(c8) * nt + i);
+                const uint4 w = __ldg(wp + static_cast<size_t>(c8) * wstride + i);
                 acc[i] = fmaf(xv[0], bf16_lo(w.x), acc[i]);
                 acc[i] = fmaf(xv[1], bf16_hi(w.x), acc[i]);
                 acc[i] = fmaf(xv[2], bf16_lo(w.y), acc[i]);

@@ -16,7 +16,7 @@ constexpr int kMaxPackItems = 64;
 struct PackItemDev {
   const float* w;
   void* packed;
-  int O, I, transpose, i_off, i_cnt, cin, dtype;
+  int O, I, transpose, i_off, i_cnt, cin, dtype, wlayout;
   int p_cout, p_cin_total, cout_pad, nt, nsrc;
   long long total;  // packed elements
 };
@@ -28,7 +28,19 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
   const PackItemDev& p = batch.it[blockIdx.y];
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < p.total; idx += static_cast<long long>(gridDim.x) * 256) {
     int co, t, tap;
-    if (p.dtype == LV_BF16) {
+    if (p.dtype == LV_BF16 && p.wlayout == LV_W_KY_STACKED) {
+      // [src][kx][chunk][ky*cout_pad + co][8]
+      long long r = idx;
+      const int e = static_cast<int>(r % 8); r /= 8;
+      const int nrow = static_cast<int>(r % (3 * p.cout_pad)); r /= 3 * p.cout_pad;
+      const int ch = p.cin / 8;
+      const int chunk = static_cast<int>(r % ch); r /= ch;
+      const int kx = static_cast<int>(r % 3); r /= 3;
+      const int s = static_cast<int>(r);
+      co = nrow % p.cout_pad;
+      tap = (nrow / p.cout_pad) * 3 + kx;
+      t = s * p.cin + chunk * 8 + e;
+    } else if (p.dtype == LV_BF16) {
       long long r = idx;
       const int e = static_cast<int>(r % 8); r /= 8;
       const int co_in = static_cast<int>(r % p.nt); r /= p.nt;
@@ -75,7 +87,7 @@ int pack_weights(const lv_pack_item* items, int count, cudaStream_t stream) {
     LV_CHECK_ARG(s.w != nullptr && s.packed != nullptr, "pack: null pointer in item %d", k);
     LV_CHECK_ARG(s.cin > 0 && s.i_cnt > 0 && s.i_off >= 0 && s.i_off + s.i_cnt <= s.I, "pack: bad slice in item %d", k);
     d.w = s.w; d.packed = s.packed; d.O = s.O; d.I = s.I; d.transpose = s.transpose; d.i_off = s.i_off;
-    d.i_cnt = s.i_cnt; d.cin = s.cin; d.dtype = s.dtype;
+    d.i_cnt = s.i_cnt; d.cin = s.cin; d.dtype = s.dtype; d.wlayout = s.wlayout;
     d.p_cout = s.transpose ? s.i_cnt : s.O;
     d.p_cin_total = s.transpose ? s.O : s.i_cnt;
     LV_CHECK_ARG(d.p_cin_total % s.cin == 0, "pack: cin_total %d not a multiple of per-source cin %d", d.p_cin_total, s.cin);
@@ -83,6 +95,8 @@ int pack_weights(const lv_pack_item* items, int count, cudaStream_t stream) {
     d.nsrc = d.p_cin_total / s.cin;
     d.cout_pad = (d.p_cout + 15) / 16 * 16;
     d.nt = pick_ntile(d.cout_pad);
+    if (s.wlayout == LV_W_KY_STACKED)
+      LV_CHECK_ARG(s.dtype == LV_BF16 && 3 * d.cout_pad <= 256, "pack: ky-stacked layout needs bf16 and cout <= 80 (item %d)", k);
     d.total = static_cast<long long>(d.cout_pad) * d.p_cin_total * 9;
     if (d.total > max_total) max_total = d.total;
   }

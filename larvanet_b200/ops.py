@@ -86,12 +86,13 @@ def pack_weights(items):
             arr[k].i_cnt = int(it.get('i_cnt', I))
             arr[k].cin = int(it['cin'])
             arr[k].dtype = dtype_id(it['dtype'])
+            arr[k].wlayout = int(it.get('wlayout', 0))
         check(lib.lv_pack_conv3x3_weights(arr, len(chunk), _stream()), 'lv_pack_conv3x3_weights')
 
 
 def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res1=None, res2=None, out=None,
                    epilogue=LV_EPI_NHWC, out_hr=None, base_hr=None, truth_hr=None, loss_sum=None, grad_sign=None,
-                   post_w=None, post_b=None, res_scale=1.0):
+                   post_w=None, post_b=None, res_scale=1.0, wlayout=0):
     """Build an lv_conv_args from torch tensors.  srcs: list of planar-8 activation tensors (same shape/dtype)."""
     x0 = srcs[0]
     dt = x0.dtype
@@ -102,6 +103,7 @@ def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res
     a.relu = int(bool(relu))
     a.epilogue = int(epilogue)
     a.res_scale = float(res_scale)
+    a.wlayout = int(wlayout)
     for i, s in enumerate(srcs):
         if tuple(s.shape) != tuple(x0.shape):
             raise _lib.LarvaNetB200Error('all conv sources must have the same shape')

@@ -24,13 +24,14 @@ def _rand_conv(rs, cout, cin_total, dtype, wscale=0.05):
     return w, b, wq
 
 
-def _pack(w, dtype, cin, transpose=0, i_off=0, i_cnt=None):
+def _pack(w, dtype, cin, transpose=0, i_off=0, i_cnt=None, wlayout=0):
     wt = torch.from_numpy(w).cuda()
     O_, I_ = w.shape[:2]
     i_cnt = I_ if i_cnt is None else i_cnt
     p_cout, p_cin_total = (i_cnt, O_) if transpose else (O_, i_cnt)
     packed = torch.zeros(ops.packed_weight_bytes(p_cout, p_cin_total, dtype), dtype=torch.uint8, device='cuda')
-    ops.pack_weights([dict(w=wt, packed=packed, transpose=transpose, i_off=i_off, i_cnt=i_cnt, cin=cin, dtype=dtype)])
+    ops.pack_weights([dict(w=wt, packed=packed, transpose=transpose, i_off=i_off, i_cnt=i_cnt, cin=cin, dtype=dtype,
+                           wlayout=wlayout)])
     return packed
 
 
@@ -256,3 +257,57 @@ def test_errors_are_loud():
                     out=act_empty(1, 8, 8, 48, torch.bfloat16))
     with pytest.raises(_lib.LarvaNetB200Error):
         ops.conv3x3([x.cpu()], torch.zeros(16, dtype=torch.uint8), 48, out=x.cpu())
+
+
+@pytest.mark.parametrize('shape', [(1, 14, 8), (2, 19, 13), (1, 5, 3), (3, 48, 48), (1, 33, 70), (1, 180, 320)])
+@pytest.mark.parametrize('simt', [False, True])
+def test_conv48_ky_stacked_layout(shape, simt):
+    """The ky-stacked tensor-core kernel (9 MMAs of N=144, row-shift epilogue) against the oracle, all epilogue paths."""
+    dtype = torch.bfloat16
+    n, h, w = shape
+    rs = np.random.RandomState(7000 + 31 * h + w)
+    wt, b, wq = _rand_conv(rs, 48, 48, dtype)
+    x, xq = _act(rs, n, 48, h, w, dtype)
+    r1, r1q = _act(rs, n, 48, h, w, dtype)
+    mk, mkq = _act(rs, n, 48, h, w, dtype)
+    packed = _pack(wt, dtype, 48, wlayout=_lib.LV_W_KY_STACKED)
+    bt = torch.from_numpy(b).cuda()
+    rtol, atol = _tol(dtype)
+    conv = O.conv2d(xq, wq, b.astype(np.float64)) if h * w <= 4096 else None
+    out = torch.empty_like(x)
+    ops.conv3x3([x], packed, 48, bias=bt, out=out, relu=True, res1=r1, simt=simt, wlayout=_lib.LV_W_KY_STACKED)
+    if conv is not None:
+        np.testing.assert_allclose(from_nhwc(out), np.maximum(conv, 0) + r1q, rtol=rtol, atol=atol)
+    else:   # full 720p frame: cross-check against the tap-major tensor-core kernel on the same operands
+        ref = torch.empty_like(x)
+        ops.conv3x3([x], _pack(wt, dtype, 48), 48, bias=bt, out=ref, relu=True, res1=r1)
+        assert (out.float() - ref.float()).abs().max().item() <= 0.0625
+    if conv is not None:
+        out2 = torch.empty_like(x)
+        ops.conv3x3([x], packed, 48, bias=None, out=out2, mask=mk, res1=r1, simt=simt, wlayout=_lib.LV_W_KY_STACKED)
+        np.testing.assert_allclose(from_nhwc(out2), O.conv2d(xq, wq) * (mkq > 0) + r1q, rtol=rtol, atol=atol)
+        # PixelShuffle(4)+base+loss epilogue and the backward-data operand in the same layout
+        base = rs.uniform(0, 255, (n, 3, 4 * h, 4 * w)).astype(np.float32)
+        out_hr = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device='cuda')
+        ops.conv3x3([x], packed, 48, bias=bt, epilogue=_lib.LV_EPI_PS4_NCHW, out_hr=out_hr,
+                    base_hr=torch.from_numpy(base).cuda(), simt=simt, wlayout=_lib.LV_W_KY_STACKED)
+        np.testing.assert_allclose(out_hr.cpu().numpy(), O.pixel_shuffle(conv, 4) + base, rtol=2e-6, atol=2e-3)
+        pk_t = _pack(wt, dtype, 48, transpose=1, wlayout=_lib.LV_W_KY_STACKED)
+        dx = torch.empty_like(x)
+        ops.conv3x3([x], pk_t, 48, bias=None, out=dx, simt=simt, wlayout=_lib.LV_W_KY_STACKED)
+        dx_ref, _, _ = O.conv2d_backward(np.zeros_like(xq), wq, xq)
+        np.testing.assert_allclose(from_nhwc(dx), dx_ref, rtol=rtol, atol=atol)
+
+
+def test_conv_ky_stacked_multi_source():
+    dtype = torch.bfloat16
+    n, h, w = 1, 30, 20
+    rs = np.random.RandomState(77)
+    wt, b, wq = _rand_conv(rs, 48, 192, dtype)
+    srcs, srcq = zip(*[_act(rs, n, 48, h, w, dtype) for _ in range(4)])
+    packed = _pack(wt, dtype, 48, wlayout=_lib.LV_W_KY_STACKED)
+    out = torch.empty_like(srcs[0])
+    ops.conv3x3(list(srcs), packed, 48, bias=torch.from_numpy(b).cuda(), out=out, wlayout=_lib.LV_W_KY_STACKED)
+    ref = O.conv2d(np.concatenate(srcq, axis=1), wq, b.astype(np.float64))
+    rtol, atol = _tol(dtype)
+    np.testing.assert_allclose(from_nhwc(out), ref, rtol=rtol, atol=atol * 2)

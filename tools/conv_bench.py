@@ -18,18 +18,19 @@ def main():
     ap.add_argument('--ctas', type=int, default=296)
     ap.add_argument('--mode', default='fwd', choices=['fwd', 'plain', 'ps', 'wgrad'])
     ap.add_argument('--splits', type=int, default=296)
+    ap.add_argument('--ky', type=int, default=0)
     a = ap.parse_args()
     g = torch.Generator(device='cuda').manual_seed(3)
     x = torch.randn((a.n, a.h, 6, a.w, 8), device='cuda', generator=g).to(torch.bfloat16)
     wt = torch.randn((48, 48, 3, 3), device='cuda', generator=g) * 0.05
     b = torch.zeros(48, device='cuda')
     packed = torch.zeros(ops.packed_weight_bytes(48, 48, torch.bfloat16), dtype=torch.uint8, device='cuda')
-    ops.pack_weights([dict(w=wt, packed=packed, cin=48, dtype=torch.bfloat16)])
+    ops.pack_weights([dict(w=wt, packed=packed, cin=48, dtype=torch.bfloat16, wlayout=a.ky)])
     o = torch.empty_like(x)
     if a.mode == 'fwd':
-        fn = lambda: ops.conv3x3([x], packed, 48, bias=b, out=o, relu=True, res1=x, max_ctas=a.ctas)
+        fn = lambda: ops.conv3x3([x], packed, 48, bias=b, out=o, relu=True, res1=x, max_ctas=a.ctas, wlayout=a.ky)
     elif a.mode == 'plain':
-        fn = lambda: ops.conv3x3([x], packed, 48, bias=b, out=o, max_ctas=a.ctas)
+        fn = lambda: ops.conv3x3([x], packed, 48, bias=b, out=o, max_ctas=a.ctas, wlayout=a.ky)
     elif a.mode == 'ps':
         hr = torch.empty((a.n, 3, 4 * a.h, 4 * a.w), device='cuda')
         base = torch.zeros_like(hr)

@@ -8,6 +8,7 @@ def main():
     n, h, w = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (8, 270, 480)
     ctas = int(sys.argv[4]) if len(sys.argv) > 4 else 296
     mode = sys.argv[5] if len(sys.argv) > 5 else 'fwd'
+    ky = int(sys.argv[6]) if len(sys.argv) > 6 else 0
     lib = _lib.load()
     lib.lv_debug_set_timeline.argtypes = [ctypes.c_void_p]
     g = torch.Generator(device='cuda').manual_seed(3)
@@ -15,9 +16,10 @@ def main():
     wt = torch.randn((48, 48, 3, 3), device='cuda', generator=g) * 0.05
     b = torch.zeros(48, device='cuda')
     packed = torch.zeros(ops.packed_weight_bytes(48, 48, torch.bfloat16), dtype=torch.uint8, device='cuda')
-    ops.pack_weights([dict(w=wt, packed=packed, cin=48, dtype=torch.bfloat16)])
+    ops.pack_weights([dict(w=wt, packed=packed, cin=48, dtype=torch.bfloat16, wlayout=ky)])
     o = torch.empty_like(x)
     kw = dict(relu=True, res1=x) if mode == 'fwd' else {}
+    kw['wlayout'] = ky
     for _ in range(3):
         ops.conv3x3([x], packed, 48, bias=b, out=o, max_ctas=ctas, **kw)
     tl = torch.zeros(9 * 64 * 4, dtype=torch.int64, device='cuda')
