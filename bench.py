@@ -281,7 +281,7 @@ def run_ours(a):
         ach = float(fl.sum() / durs.sum() / 1e12)
         peak = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
         line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                            'traffic': None, 'kernel': 'conv3x3_tc_kernel<48,48> (fwd + backward-data launches)',
+                            'traffic': None, 'kernel': 'conv3x3_chain_kernel<48,48> (forward and backward-data conv chains, one persistent launch each)',
                             'launches_timed': len(recs), 'avg_launch_us': float(durs.mean() * 1e6),
                             'peak_source': peaks_src + ', sustained bf16 (kernel timed inside a long step)'}
         line['clocks'] = clocks

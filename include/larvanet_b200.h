@@ -135,6 +135,22 @@ int lv_conv3x3(const lv_conv_args* args, int max_ctas, void* stream);
 int lv_conv3x3_simt(const lv_conv_args* args, void* stream);
 
 /*
+ * A chain of convolutions in ONE persistent launch: layers[0..count) are executed in order as if by `count` calls of
+ * lv_conv3x3, but the CTAs stay resident and the layers are linked by per-tile data-flow flags instead of kernel
+ * boundaries (no launch, prologue or pipeline drain per layer).  Replaces the Conv2d sequences of
+ * models/LarvaNet.py:116-140 (ResidualBlock / LarvaBody) and :178-201 (LarvaLeg), forward and input-gradient.
+ *   layers:  HOST array (copied by value into the launch), 1 <= count <= 64; every layer must be a single-source
+ *            LV_BF16 48 -> 48 conv with LV_W_TAP_MAJOR weights and 16-byte aligned bias, all on the same (n, h, w).
+ *            A layer may read (src / res1 / res2 / mask) anything written by an EARLIER layer of the chain or before
+ *            the call, and may overwrite any buffer whose readers are earlier layers.
+ *   sync_ws: device workspace of lv_conv_chain_workspace_bytes(n, h, w) bytes; zero it once after allocation, the
+ *            kernel leaves it zeroed.  One workspace per stream.
+ */
+int64_t lv_conv_chain_workspace_bytes(int n, int h, int w);
+int lv_conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, int64_t sync_ws_bytes, int max_ctas,
+                     void* stream);
+
+/*
  * LarvaHead conv (3->cout, fp32 math) fused with the bicubic x4 base.
  * Replaces models/LarvaNet.py:227,231-233 (LarvaHead) and :283-285 (F.interpolate bicubic, align_corners=False);
  * for EDSR (`pre_w`/`pre_b` non-NULL) also the 1x1 MeanShift before first_conv (models/edsr.py:197-198).

@@ -66,6 +66,8 @@ SIGNATURES = {
     'lv_pack_conv3x3_weights': (C.c_int, [C.POINTER(PackItem), C.c_int, C.c_void_p]),
     'lv_conv3x3': (C.c_int, [C.POINTER(ConvArgs), C.c_int, C.c_void_p]),
     'lv_conv3x3_simt': (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    'lv_conv_chain_workspace_bytes': (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    'lv_conv3x3_chain': (C.c_int, [C.POINTER(ConvArgs), C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     'lv_head_bicubic_fwd': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p]),
     'lv_bicubic_x4': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'lv_head_wgrad': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_float, C.c_void_p]),

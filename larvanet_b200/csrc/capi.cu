@@ -37,6 +37,9 @@ int sm_count() {
 int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
 int conv3x3_tc_ky(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
 int conv3x3_simt(const lv_conv_args& a, cudaStream_t stream);
+long long conv3x3_chain_workspace_bytes(int n, int h, int w);
+int conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
+                  cudaStream_t stream);
 int pick_ntile(int cout_pad);
 extern long long* g_timeline;
 extern int g_use_pdl;
@@ -134,6 +137,23 @@ int lv_conv3x3(const lv_conv_args* a, int max_ctas, void* stream) {
     return conv3x3_tc(*a, max_ctas, static_cast<cudaStream_t>(stream));
   }
   return conv3x3_simt(*a, static_cast<cudaStream_t>(stream));
+}
+
+int64_t lv_conv_chain_workspace_bytes(int n, int h, int w) {
+  if (n < 0 || h < 0 || w < 0) return -1;
+  return conv3x3_chain_workspace_bytes(n, h, w);
+}
+
+int lv_conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, int64_t sync_ws_bytes, int max_ctas,
+                     void* stream) {
+  LV_CHECK_ARG(layers != nullptr && count >= 1, "conv chain: no layers");
+  for (int i = 0; i < count; ++i) {
+    int rc = check_conv(&layers[i]);
+    if (rc != LV_OK) return rc;
+    LV_CHECK_ARG(layers[i].bias == nullptr || (reinterpret_cast<uintptr_t>(layers[i].bias) & 15u) == 0,
+                 "conv chain: layer %d bias is not 16-byte aligned", i);
+  }
+  return conv3x3_chain(layers, count, sync_ws, sync_ws_bytes, max_ctas, static_cast<cudaStream_t>(stream));
 }
 
 int lv_conv3x3_simt(const lv_conv_args* a, void* stream) {

@@ -124,6 +124,11 @@ class LarvaEngine:
         self._infer = {}   # shape -> (bufs, graph)
         self._train = {}
         self.simt = False  # tests flip this to cross-check the tensor-core kernels on CUDA cores
+        # consecutive 48->48 convs run as ONE persistent data-flow launch (ops.conv3x3_chain); LARVANET_B200_CHAIN=0
+        # falls back to one launch per conv
+        self.use_chain = os.environ.get('LARVANET_B200_CHAIN', '1') != '0'
+        self._chain = None      # list of pending ConvArgs while a chain is being recorded
+        self._chain_ws = {}     # (n, h, w) -> flag workspace
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (lv_launch_count only sees eager ones)
         # data parallel
         self.world_size = 1
@@ -186,11 +191,37 @@ class LarvaEngine:
 
     def _conv(self, srcs, prefix, out=None, **kw):
         _, b = self._w(prefix)
-        ops.conv3x3(srcs, self._pk[(prefix, 'fwd')], C, bias=b, out=out, max_ctas=self.max_ctas, simt=self.simt, **kw)
+        self._emit(ops.make_conv_args(srcs, self._pk[(prefix, 'fwd')], C, bias=b, out=out, **kw))
 
     def _dgrad(self, dy, prefix, out, s=0, **kw):
-        ops.conv3x3([dy], self._pk[(prefix, 'bwd', s)], C, bias=None, out=out, max_ctas=self.max_ctas, simt=self.simt,
-                    **kw)
+        self._emit(ops.make_conv_args([dy], self._pk[(prefix, 'bwd', s)], C, bias=None, out=out, **kw))
+
+    def _emit(self, args):
+        """Launch one conv, or queue it while a chain is being recorded (flushed by the first conv that cannot join)."""
+        if self._chain is not None and ops.chain_eligible(args):
+            self._chain.append(args)
+            return
+        self._flush_chain()
+        ops.conv3x3_launch(args, self.max_ctas, self.simt)
+
+    def _begin_chain(self):
+        on = self.use_chain and not self.simt and self.act_dtype == torch.bfloat16
+        self._chain = [] if on else None
+
+    def _flush_chain(self, end=False):
+        pending = self._chain
+        if pending:
+            self._chain = []
+            if len(pending) == 1:
+                ops.conv3x3_launch(pending[0], self.max_ctas, self.simt)
+            else:
+                a0 = pending[0]
+                key = (a0.n, a0.h, a0.w)
+                if key not in self._chain_ws:
+                    self._chain_ws[key] = ops.chain_workspace(a0.n, a0.h, a0.w, self.device)
+                ops.conv3x3_chain(pending, self._chain_ws[key], self.max_ctas)
+        if end:
+            self._chain = None
 
     def _act(self, n, h, w, c=C):
         return ops.act_empty(n, h, w, c, self.act_dtype, self.device)
@@ -216,6 +247,7 @@ class LarvaEngine:
         if k == 0:
             b.out.copy_(b.base)
             return
+        self._begin_chain()
         fin = b.f0
         for i in range(k):
             a = fin
@@ -238,6 +270,7 @@ class LarvaEngine:
             p = f'body_{k - 1}.leg.recon_block'
             self._conv([fin], p + '.0', out=b.u, relu=True)
             self._conv([b.u], p + '.2', epilogue=LV_EPI_PS4_NCHW, out_hr=b.out, base_hr=b.base)
+        self._flush_chain(end=True)
 
     def forward(self, x, exit_leg=None):
         """x: fp32 NCHW [n,3,h,w] CUDA tensor on the 0..255 scale -> fp32 NCHW [n,3,4h,4w] (engine-owned buffer)."""
@@ -341,6 +374,7 @@ class LarvaEngine:
         b.loss_sum.zero_()
         self.arena.grad.zero_()
         ops.head_bicubic(b.x, hw, hb, b.f0, b.base)
+        self._begin_chain()
         # ---------------- forward ----------------
         fin = b.f0
         for i, nb in enumerate(self.blocks):
@@ -365,12 +399,15 @@ class LarvaEngine:
                        loss_sum=b.loss_sum, grad_sign=b.gt,
                        out_hr=b.exits[self.m] if b.exits is not None else None)
         # ---------------- backward ----------------
+        # (the weight-gradient batches only read saved activations and dY buffers, so they run after the whole
+        # backward-data chain)
+        wgrads = []
         if self.v2:
             self._dgrad(b.gt, 'tail.recon_block.2', out=b.dut, mask=b.ut)
             self._dgrad(b.dut, 'tail.recon_block.0', out=b.dmf)
             for s in range(self.m):
                 self._dgrad(b.dmf, 'tail.merge_conv', out=b.dfeat[s], s=s)
-            b.wgrad_tail.launch(simt=self.simt)
+            wgrads.append(b.wgrad_tail)
         dnext = None
         for i in reversed(range(self.m)):
             nb = self.blocks[i]
@@ -385,7 +422,10 @@ class LarvaEngine:
                 dst = b.dfin[i] if j == 0 else b.da[i][j - 1]
                 self._dgrad(b.dt[i][j], pj + '.0', out=dst, res1=b.da[i][j], res2=dfout if j == 0 else None)
             dnext = b.dfin[i]
-            b.wgrad[i].launch(simt=self.simt)
+            wgrads.append(b.wgrad[i])
+        self._flush_chain(end=True)
+        for wb in wgrads:
+            wb.launch(simt=self.simt)
         ops.head_wgrad(b.x, b.dfin[0], self.arena.grad_views['head.feature_extraction.weight'],
                        self.arena.grad_views['head.feature_extraction.bias'], scale)
 

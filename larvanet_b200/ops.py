@@ -149,6 +149,40 @@ def conv3x3(srcs, weights, cout, max_ctas=0, simt=False, **kw):
     conv3x3_launch(make_conv_args(srcs, weights, cout, **kw), max_ctas, simt)
 
 
+def chain_workspace(n, h, w, device):
+    """Zeroed data-flow flag workspace for `conv3x3_chain` on activations of n x h x w (one per stream)."""
+    nbytes = int(_lib.load().lv_conv_chain_workspace_bytes(int(n), int(h), int(w)))
+    return torch.zeros(max(nbytes // 4, 1), dtype=torch.int32, device=device)
+
+
+def chain_eligible(args):
+    """True when `args` (ConvArgs) can be a layer of `conv3x3_chain`."""
+    return (args.dtype == _lib.LV_BF16 and args.cin == 48 and args.num_src == 1 and args.cout == 48
+            and args.wlayout == _lib.LV_W_TAP_MAJOR)
+
+
+def conv3x3_chain(arg_list, workspace, max_ctas=0):
+    """Run the convs described by `arg_list` (ConvArgs from make_conv_args, in order) as ONE persistent launch."""
+    lib = _lib.load()
+    n = len(arg_list)
+    if n == 0:
+        return
+    pos = 0
+    while pos < n:   # the C-ABI takes at most 64 layers per launch
+        cnt = min(64, n - pos)
+        arr = (_lib.ConvArgs * cnt)(*arg_list[pos:pos + cnt])
+        if CONV_TIMERS is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(lib.lv_conv3x3_chain(arr, cnt, workspace.data_ptr(), workspace.numel() * 4, int(max_ctas), _stream()),
+              'lv_conv3x3_chain')
+        if CONV_TIMERS is not None:
+            e1.record()
+            a0 = arr[0]
+            CONV_TIMERS.append((e0, e1, 2.0 * 9 * 48 * 48 * a0.n * a0.h * a0.w * cnt, ('chain', cnt, 0)))
+        pos += cnt
+
+
 def head_bicubic(x, w, b, fea, base_hr=None, pre_w=None, pre_b=None):
     """x fp32 NCHW [n,3,h,w] -> fea NHWC [n,h,w,cout] (+ base_hr fp32 NCHW [n,3,4h,4w])."""
     n, c, h, wd = (int(v) for v in x.shape)

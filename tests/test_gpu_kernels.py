@@ -311,3 +311,77 @@ def test_conv_ky_stacked_multi_source():
     ref = O.conv2d(np.concatenate(srcq, axis=1), wq, b.astype(np.float64))
     rtol, atol = _tol(dtype)
     np.testing.assert_allclose(from_nhwc(out), ref, rtol=rtol, atol=atol * 2)
+
+
+def _chain_layers(rs, n, h, w, depth):
+    """A LarvaNet-like layer list on ping-pong buffers: resblocks (relu conv, conv + skips), a leg with PixelShuffle +
+    loss epilogue, and masked input-gradient style layers.  Returns (make_args(bufs) -> [ConvArgs], make_bufs)."""
+    dtype = torch.bfloat16
+    convs = []
+    for _ in range(8):
+        wt, b, _ = _rand_conv(rs, 48, 48, dtype, wscale=0.04)
+        convs.append((_pack(wt, dtype, 48), torch.from_numpy(b).cuda()))
+    x0, _ = _act(rs, n, 48, h, w, dtype)
+    base = torch.from_numpy(rs.uniform(0, 255, (n, 3, 4 * h, 4 * w)).astype(np.float32)).cuda()
+    truth = torch.from_numpy(rs.uniform(0, 255, (n, 3, 4 * h, 4 * w)).astype(np.float32)).cuda()
+
+    def make_bufs():
+        z = lambda: torch.zeros_like(x0)
+        return dict(x=x0.clone(), t=z(), a=z(), b=z(), u=z(), d=z(), g=z(),
+                    hr=torch.zeros_like(base), loss=torch.zeros(1, dtype=torch.float64, device='cuda'))
+
+    def make_args(B):
+        L = []
+        cv = lambda i, src, **kw: L.append(ops.make_conv_args([src], convs[i % 8][0], 48, bias=convs[i % 8][1], **kw))
+        cur, nxt = B['x'], B['a']
+        for blk in range(depth):
+            cv(2 * blk, cur, out=B['t'], relu=True)                                     # t is rewritten every block (WAR)
+            cv(2 * blk + 1, B['t'], out=nxt, res1=cur, res2=B['x'] if blk % 2 else None)
+            cur, nxt = nxt, (B['b'] if nxt is B['a'] else B['a'])
+        cv(5, cur, out=B['u'], relu=True)
+        cv(6, B['u'], epilogue=_lib.LV_EPI_PS4_NCHW, out_hr=B['hr'], base_hr=base, truth_hr=truth, loss_sum=B['loss'],
+           grad_sign=B['g'])
+        cv(7, B['g'], out=B['d'], mask=B['u'])                                          # dgrad-style: ReLU mask of a saved act
+        cv(3, B['d'], out=B['t'], res1=B['g'])
+        return L
+    return make_args, make_bufs
+
+
+@pytest.mark.parametrize('shape,ctas', [((2, 37, 45), 0), ((16, 48, 48), 0), ((1, 180, 320), 0), ((3, 20, 9), 5),
+                                        ((1, 16, 8), 0)])
+def test_conv_chain_matches_sequential(shape, ctas):
+    """lv_conv3x3_chain (one persistent data-flow launch) == the same layers launched one by one, bit for bit; repeated
+    launches reuse the self-cleaning flag workspace."""
+    n, h, w = shape
+    rs = np.random.RandomState(5)
+    make_args, make_bufs = _chain_layers(rs, n, h, w, depth=5)
+    ref = make_bufs()
+    for a in make_args(ref):
+        ops.conv3x3_launch(a)
+    torch.cuda.synchronize()
+    ws = ops.chain_workspace(n, h, w, 'cuda')
+    for rep in range(3):
+        got = make_bufs()
+        ops.conv3x3_chain(make_args(got), ws, max_ctas=ctas)
+        torch.cuda.synchronize()
+        assert int(ws.abs().sum().item()) == 0, 'flag workspace not re-zeroed'
+        for k in ref:
+            if k == 'loss':
+                assert abs(got[k].item() - ref[k].item()) <= 1e-7 * abs(ref[k].item())   # fp32 partial sums regroup
+            else:
+                assert torch.equal(got[k], ref[k]), f'buffer {k} differs (rep {rep})'
+
+
+def test_conv_chain_rejects_bad_layers():
+    rs = np.random.RandomState(6)
+    make_args, make_bufs = _chain_layers(rs, 1, 16, 8, depth=1)
+    B = make_bufs()
+    L = make_args(B)
+    ws = ops.chain_workspace(1, 16, 8, 'cuda')
+    bad = ops.make_conv_args([B['x']], L[0].weights and _pack(_rand_conv(rs, 48, 48, torch.bfloat16)[0], torch.bfloat16, 48),
+                             48, out=B['t'])
+    bad.h = 15
+    with pytest.raises(_lib.LarvaNetB200Error):
+        ops.conv3x3_chain([L[0], bad], ws)
+    with pytest.raises(_lib.LarvaNetB200Error):
+        ops.conv3x3_chain(L, torch.zeros(1, dtype=torch.int32, device='cuda'))

@@ -19,6 +19,8 @@ def main():
     ap.add_argument('--mode', default='fwd', choices=['fwd', 'plain', 'ps', 'wgrad'])
     ap.add_argument('--splits', type=int, default=296)
     ap.add_argument('--ky', type=int, default=0)
+    ap.add_argument('--chain', type=int, default=0, help='time ONE lv_conv3x3_chain launch of this many dependent convs')
+    ap.add_argument('--graph', type=int, default=0, help='time a CUDA graph of this many DEPENDENT convs (ping-pong)')
     a = ap.parse_args()
     g = torch.Generator(device='cuda').manual_seed(3)
     x = torch.randn((a.n, a.h, 6, a.w, 8), device='cuda', generator=g).to(torch.bfloat16)
@@ -40,6 +42,34 @@ def main():
         db = torch.zeros(48, device='cuda')
         batch = ops.WgradBatch([dict(x=x, dy=o.copy_(x), dw=dw, db=db)], splits=a.splits, device='cuda')
         fn = batch.launch
+    if a.chain:
+        o2 = torch.empty_like(x)
+        bufs = [o, o2]
+        L, src = [], x
+        for i in range(a.chain):
+            dst = bufs[i & 1]
+            L.append(ops.make_conv_args([src], packed, 48, bias=b, out=dst, relu=(i & 1) == 0,
+                                        res1=None if (i & 1) == 0 else x))
+            src = dst
+        ws = ops.chain_workspace(a.n, a.h, a.w, 'cuda')
+        fn = lambda: ops.conv3x3_chain(L, ws, max_ctas=a.ctas)
+        a.graph = 0
+    if a.graph:
+        o2 = torch.empty_like(x)
+        bufs = [o, o2]
+        def chain():
+            src = x
+            for i in range(a.graph):
+                dst = bufs[i & 1]
+                ops.conv3x3([src], packed, 48, bias=b, out=dst, relu=(i & 1) == 0, res1=None if (i & 1) == 0 else x,
+                            max_ctas=a.ctas, wlayout=a.ky)
+                src = dst
+        chain()
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            chain()
+        fn = gr.replay
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -49,7 +79,7 @@ def main():
         fn()
     e1.record()
     torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) / a.iters * 1e3
+    us = e0.elapsed_time(e1) / a.iters * 1e3 / max(a.graph, a.chain, 1)
     fl = 2 * 20736 * a.n * a.h * a.w
     print(f'{a.mode} n={a.n} {a.h}x{a.w} ctas={a.ctas}: {us:.1f} us/launch  {fl / us * 1e-6:.1f} TFLOP/s')
 
