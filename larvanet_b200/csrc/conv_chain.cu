@@ -35,9 +35,10 @@ namespace chain {
 constexpr int kMaxLayers = 64;
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2, kHaloPix = kHaloW * kHaloH;  // 10 x 18 = 180
-constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 96;
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 64;
 constexpr int kMmaWarp = kEpiWarps;
-constexpr int kThreads = kEpiThreads + 32 + kProdThreads;  // 384 (<= 168 registers per thread)
+constexpr int kPubWarp = kMmaWarp + 1 + kProdThreads / 32;    // warp 11: publishes finished tiles
+constexpr int kThreads = kEpiThreads + 32 + kProdThreads + 32;  // 384 = 3 warps per scheduler (<= 168 registers per thread)
 constexpr int kWBufs = 3;
 constexpr uint32_t kWarpsPerTile = 4;                      // epilogue warps per (layer, tile) = done[] increments
 
@@ -101,8 +102,10 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 + s); };
   auto wfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 4 + b); };
   auto wfree_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 4 + kWBufs + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4 + 2 * kWBufs);
+  auto pub_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 4 + 2 * kWBufs + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4 + 2 * kWBufs + 2);
   uint32_t* s_last = tmem_slot + 1;
+  volatile uint32_t* pub_seen = tmem_slot + 2;   // jobs whose completion the publisher warp has observed
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -117,6 +120,8 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
       mbar_init(wfull_bar(b), 1);
       mbar_init(wfree_bar(b), 1);
     }
+    for (int s = 0; s < 2; ++s) mbar_init(pub_bar(s), kEpiWarps / 2);
+    tmem_slot[2] = 0u;
     mbar_fence_init();
   }
   if (warp == kMmaWarp) tmem_alloc<C_::TMEM_COLS>(smem_u32(tmem_slot));
@@ -135,7 +140,22 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
     return (static_cast<int>(blockIdx.x) + G - sh) % G;
   };
 
-  if (warp > kMmaWarp) {
+  if (warp == kPubWarp) {
+    // =============================== publisher: GPU-scope release of finished tiles ===============================
+    // The epilogue warps arrive on a CTA-scope mbarrier after their stores and go on to the next tile; this warp turns
+    // "all 4 warps of the tile arrived" into ONE red.release.gpu (which is what waits for the store acknowledgements).
+    if (lane == 0) {
+      uint32_t k = 0;
+      for (int l = 0; l < nlayers; ++l) {
+        for (int tile = first_tile(l); tile < g.total_tiles; tile += G, ++k) {
+          mbar_wait(pub_bar(k & 1u), (k >> 1) & 1u);
+          *pub_seen = k + 1u;
+          red_release_gpu_add(done + tile, kWarpsPerTile);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp > kMmaWarp) {
     // =============================== producers: dependency wait + halo tiles -> smem ===============================
     const int ptid = threadIdx.x - (kEpiThreads + 32);
     uint32_t pc_dst[C_::PROD_PIECES];
@@ -313,6 +333,13 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
             for (int j = 0; j < NCH; ++j) qb[j] = ldcg16(opb + o0 + j * chunk_stride);
           }
         }
+        // phase-parity safety of pub_bar: the publisher must have seen this stage's previous tile (always true in practice)
+        if (lane == 0 && k >= 2) {
+          uint32_t spins = 0;
+          while (*pub_seen + 1u < k) {
+            if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+          }
+        }
         if (tl0) tl_stamp(g, 2, k, 0);
         mbar_wait_relaxed(tfull_bar(as), (k >> 1) & 1);
         tc_fence_after_sync();
@@ -373,10 +400,9 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
           tc_fence_before_sync();
           mbar_arrive(tempty_bar(as));
         }
-        // publish: this warp's quarter of (layer l, tile) is in global memory (each warp releases its own stores, so
-        // nothing waits for the slowest warp and there is no intra-CTA hand-over on the dependency path)
+        // this warp's quarter of (layer l, tile) is on its way to global memory: hand it to the publisher warp
         __syncwarp();
-        if (lane == 0) red_release_gpu_add(done + tile, 1u);
+        if (lane == 0) mbar_arrive(pub_bar(as));
         if (tl0) tl_stamp(g, 2, k, 3);
       }
       if (a.truth_hr != nullptr && a.loss_sum != nullptr) {
