@@ -72,6 +72,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_relaxed_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t need) {
   uint32_t spins = 0;
   while (ld_acquire_gpu(p) < need) {
@@ -81,6 +84,88 @@ __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t need) {
 }
 __device__ __forceinline__ uint4 ldcg16(const __nv_bfloat16* p) {
   return __ldcg(reinterpret_cast<const uint4*>(p));   // L2 only: other CTAs rewrite these buffers during the kernel
+}
+
+// Fast planar epilogue of one tile for one thread (one pixel x NT channels), straight-line for a compile-time flag
+// set EPI (bit0 ReLU, bit1 ReLU-mask, bit2 res1, bit3 res2; EPI < 0: flags read at run time).  Operand loads are
+// issued before the accumulator wait so that their latency hides behind the MMAs.
+struct FastEpi {
+  const __nv_bfloat16* mask;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+  __nv_bfloat16* out;
+  float res_scale;
+  int relu;
+};
+
+template <int EPI, int NT>
+__device__ __forceinline__ void fast_tile(const FastEpi& e, const float* breg, bool valid, size_t o0, size_t chunk_stride,
+                                          uint32_t taddr, uint32_t tfull, uint32_t tempty, uint32_t parity) {
+  constexpr int NCH = NT / 8;
+  const bool unit_scale = (EPI >= 0) || (e.res_scale == 1.0f);
+  const bool do_relu = (EPI >= 0) ? ((EPI & 1) != 0) : (e.relu != 0);
+  const bool do_mask = (EPI >= 0) ? ((EPI & 2) != 0) : (e.mask != nullptr);
+  const bool do_res1 = (EPI >= 0) ? ((EPI & 4) != 0) : (e.res1 != nullptr);
+  const bool do_res2 = (EPI >= 0) ? ((EPI & 8) != 0) : (e.res2 != nullptr);
+  uint4 qm[NCH], q1[NCH], q2[NCH];
+  if (valid) {
+    if (do_mask) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) qm[j] = ldcg16(e.mask + o0 + j * chunk_stride);
+    }
+    if (do_res1) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) q1[j] = ldcg16(e.res1 + o0 + j * chunk_stride);
+    }
+    if (do_res2) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) q2[j] = ldcg16(e.res2 + o0 + j * chunk_stride);
+    }
+  }
+  mbar_wait_relaxed(tfull, parity);
+  tc_fence_after_sync();
+  float v[NT];
+#pragma unroll
+  for (int j = 0; j < NT / 16; ++j) tmem_ld16(taddr + j * 16, v + j * 16);
+  tmem_ld_wait();
+  tc_fence_before_sync();
+  mbar_arrive(tempty);   // accumulator stage free: this stage's next tile may be accumulated
+  if (valid) {
+    __nv_bfloat16* po = e.out + o0;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float* vj = v + 8 * j;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vj[i] += breg[8 * j + i];
+      if (!unit_scale) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vj[i] *= e.res_scale;
+      }
+      if (do_relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vj[i] = fmaxf(vj[i], 0.f);
+      }
+      if (do_mask) {
+        const uint32_t w4[4] = {qm[j].x, qm[j].y, qm[j].z, qm[j].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          vj[2 * t] = (bf16_lo(w4[t]) > 0.f) ? vj[2 * t] : 0.f;
+          vj[2 * t + 1] = (bf16_hi(w4[t]) > 0.f) ? vj[2 * t + 1] : 0.f;
+        }
+      }
+      if (do_res1) {
+        const uint32_t w4[4] = {q1[j].x, q1[j].y, q1[j].z, q1[j].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { vj[2 * t] += bf16_lo(w4[t]); vj[2 * t + 1] += bf16_hi(w4[t]); }
+      }
+      if (do_res2) {
+        const uint32_t w4[4] = {q2[j].x, q2[j].y, q2[j].z, q2[j].w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { vj[2 * t] += bf16_lo(w4[t]); vj[2 * t + 1] += bf16_hi(w4[t]); }
+      }
+      store8(po + j * chunk_stride, vj);
+    }
+  }
 }
 
 template <int CIN, int NT, int NSTAGE>
@@ -103,7 +188,7 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
   auto wfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 4 + b); };
   auto wfree_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 4 + kWBufs + b); };
   auto pub_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 4 + 2 * kWBufs + s); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4 + 2 * kWBufs + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4 + 2 * kWBufs + 4);
   uint32_t* s_last = tmem_slot + 1;
   volatile uint32_t* pub_seen = tmem_slot + 2;   // jobs whose completion the publisher warp has observed
 
@@ -120,7 +205,7 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
       mbar_init(wfull_bar(b), 1);
       mbar_init(wfree_bar(b), 1);
     }
-    for (int s = 0; s < 2; ++s) mbar_init(pub_bar(s), kEpiWarps / 2);
+    for (int s = 0; s < 4; ++s) mbar_init(pub_bar(s), kEpiWarps / 2);
     tmem_slot[2] = 0u;
     mbar_fence_init();
   }
@@ -145,13 +230,24 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
     // The epilogue warps arrive on a CTA-scope mbarrier after their stores and go on to the next tile; this warp turns
     // "all 4 warps of the tile arrived" into ONE red.release.gpu (which is what waits for the store acknowledgements).
     if (lane == 0) {
+      int l = 0, tile = first_tile(0);
       uint32_t k = 0;
-      for (int l = 0; l < nlayers; ++l) {
-        for (int tile = first_tile(l); tile < g.total_tiles; tile += G, ++k) {
-          mbar_wait(pub_bar(k & 1u), (k >> 1) & 1u);
-          *pub_seen = k + 1u;
-          red_release_gpu_add(done + tile, kWarpsPerTile);
+      auto advance = [&]() {
+        tile += G;
+        ++k;
+        while (l < nlayers && tile >= g.total_tiles) {
+          ++l;
+          if (l < nlayers) tile = first_tile(l);
         }
+      };
+      while (l < nlayers) {
+        mbar_wait(pub_bar(k & 3u), (k >> 2) & 1u);
+        const int t0 = tile;
+        advance();
+        *pub_seen = k;
+        tl_stamp(g, 3, k - 1, 0);
+        red_release_gpu_add(done + t0, kWarpsPerTile);
+        tl_stamp(g, 3, k - 1, 1);
       }
     }
     __syncwarp();
@@ -291,16 +387,21 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
     uint32_t k = 0;   // CTA-local job counter; this group handles the jobs with k % 2 == eg
     for (int l = 0; l < nlayers; ++l) {
       const lv_conv_args& a = P.layer[l];
-      const bool do_relu = (a.relu != 0), do_mask = (a.mask != nullptr);
-      const bool do_res1 = (a.res1 != nullptr), do_res2 = (a.res2 != nullptr);
-      // operand A = ReLU mask or first residual (never both in LarvaNet's graphs; both present -> generic path)
-      const bool fast = (a.epilogue == LV_EPI_NHWC) && (a.cout == NT) && !(do_mask && do_res1);
-      const bool unit_scale = (a.res_scale == 1.0f);
-      const __nv_bfloat16* opa = reinterpret_cast<const __nv_bfloat16*>(do_mask ? a.mask : a.res1);
-      const __nv_bfloat16* opb = reinterpret_cast<const __nv_bfloat16*>(a.res2);
-      const bool has_a = (do_mask || do_res1), has_b = do_res2;
-      __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(a.out);
-      const float rs = a.res_scale;
+      const bool fast = (a.epilogue == LV_EPI_NHWC) && (a.cout == NT);
+      const bool has_ops = (a.mask != nullptr) || (a.res1 != nullptr) || (a.res2 != nullptr);
+      FastEpi fe;
+      fe.mask = reinterpret_cast<const __nv_bfloat16*>(a.mask);
+      fe.res1 = reinterpret_cast<const __nv_bfloat16*>(a.res1);
+      fe.res2 = reinterpret_cast<const __nv_bfloat16*>(a.res2);
+      fe.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+      fe.res_scale = a.res_scale;
+      fe.relu = a.relu;
+      // straight-line epilogues for the flag sets LarvaNet's graphs use; anything else reads the flags at run time
+      int epi = -1;
+      if (fast && a.res_scale == 1.0f) {
+        const int code = (a.relu ? 1 : 0) | (a.mask ? 2 : 0) | (a.res1 ? 4 : 0) | (a.res2 ? 8 : 0);
+        if (code == 0 || code == 1 || code == 2 || code == 4 || code == 12) epi = code;
+      }
       float loss = 0.f;
       float breg[NT];
 #pragma unroll
@@ -317,79 +418,29 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
         const int y = tyi * kTileH + r, x = (rem - tyi * g.tiles_x) * kTileW + c;
         const bool valid = (y < H) && (x < W);
         const size_t o0 = valid ? act_off(n, y, x, 0, H, W, NCH) : 0;
-        uint4 qa[NCH], qb[NCH];
-        if (l > 0 && (!fast || has_a || has_b)) {
+        // pub_bar ring safety: the publisher must have seen this barrier's previous use (job k-4); read the counter
+        // now, test it after the stores
+        const uint32_t seen = *pub_seen;
+        if (l > 0 && (epi < 0 || has_ops)) {
           // same-tile operands come from earlier layers of this chain, possibly written by another CTA
           if (lane == 0) wait_flag(done + tile, kWarpsPerTile * static_cast<uint32_t>(l));
           __syncwarp();
         }
-        if (fast && valid) {
-          if (has_a) {
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) qa[j] = ldcg16(opa + o0 + j * chunk_stride);
-          }
-          if (has_b) {
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) qb[j] = ldcg16(opb + o0 + j * chunk_stride);
-          }
-        }
-        // phase-parity safety of pub_bar: the publisher must have seen this stage's previous tile (always true in practice)
-        if (lane == 0 && k >= 2) {
-          uint32_t spins = 0;
-          while (*pub_seen + 1u < k) {
-            if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
-          }
-        }
         if (tl0) tl_stamp(g, 2, k, 0);
-        mbar_wait_relaxed(tfull_bar(as), (k >> 1) & 1);
-        tc_fence_after_sync();
-        if (tl0) tl_stamp(g, 2, k, 1);
-        if (fast) {
-          float v[NT];
-#pragma unroll
-          for (int j = 0; j < NT / 16; ++j) tmem_ld16(taddr + j * 16, v + j * 16);
-          tmem_ld_wait();
-          tc_fence_before_sync();
-          mbar_arrive(tempty_bar(as));
-          if (tl0) tl_stamp(g, 2, k, 2);
-          if (valid) {
-            __nv_bfloat16* po = outp + o0;
-#pragma unroll
-            for (int j = 0; j < NCH; ++j) {
-              float* vj = v + 8 * j;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) vj[i] += breg[8 * j + i];
-              if (!unit_scale) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vj[i] *= rs;
-              }
-              if (do_relu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) vj[i] = fmaxf(vj[i], 0.f);
-              }
-              if (has_a) {
-                const uint32_t w4[4] = {qa[j].x, qa[j].y, qa[j].z, qa[j].w};
-                if (do_mask) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    vj[2 * e] = (bf16_lo(w4[e]) > 0.f) ? vj[2 * e] : 0.f;
-                    vj[2 * e + 1] = (bf16_hi(w4[e]) > 0.f) ? vj[2 * e + 1] : 0.f;
-                  }
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) { vj[2 * e] += bf16_lo(w4[e]); vj[2 * e + 1] += bf16_hi(w4[e]); }
-                }
-              }
-              if (has_b) {
-                const uint32_t w4[4] = {qb[j].x, qb[j].y, qb[j].z, qb[j].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { vj[2 * e] += bf16_lo(w4[e]); vj[2 * e + 1] += bf16_hi(w4[e]); }
-              }
-              store8(po + j * chunk_stride, vj);
-            }
+        const uint32_t par = (k >> 1) & 1;
+        if (epi >= 0) {
+          switch (epi) {
+            case 0: fast_tile<0, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
+            case 1: fast_tile<1, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
+            case 2: fast_tile<2, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
+            case 4: fast_tile<4, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
+            case 12: fast_tile<12, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
+            default: break;
           }
         } else {
-          // PixelShuffle / mask+residual epilogues: shared 16-channel routine
+          // PixelShuffle and unusual flag sets: shared 16-channel routine
+          mbar_wait_relaxed(tfull_bar(as), par);
+          tc_fence_after_sync();
 #pragma unroll 1
           for (int j = 0; j < NT / 16; ++j) {
             float v[16];
@@ -402,7 +453,15 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
         }
         // this warp's quarter of (layer l, tile) is on its way to global memory: hand it to the publisher warp
         __syncwarp();
-        if (lane == 0) mbar_arrive(pub_bar(as));
+        if (lane == 0) {
+          if (k >= 4 && seen + 3u < k) {
+            uint32_t spins = 0;
+            while (*pub_seen + 3u < k) {
+              if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+            }
+          }
+          mbar_arrive(pub_bar(k & 3u));
+        }
         if (tl0) tl_stamp(g, 2, k, 3);
       }
       if (a.truth_hr != nullptr && a.loss_sum != nullptr) {

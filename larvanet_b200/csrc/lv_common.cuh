@@ -200,6 +200,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe of a phase
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded spin: a protocol bug must surface as a trapped kernel (CUDA error at the next sync), never as a hung GPU.
 #ifndef LV_SPIN_LIMIT
 #define LV_SPIN_LIMIT (1u << 22)

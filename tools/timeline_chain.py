@@ -34,7 +34,7 @@ def main():
     t = tl.cpu().view(9, 64, 4)
     t0 = int(t[t > 0].min())
     names = {0: ('prod', ['deps_ok', 'got_empty', 'issued', 'polled']),
-             3: ('pub ', ['last_in', '-', 'flagged', '-']),
+             3: ('pub ', ['arrived', 'released', '-', '-']),
              4: ('st h0', ['q0', 'q1', 'q2', 'q3']), 5: ('st h1', ['q0', 'q1', 'q2', 'q3']),
              6: ('rl h0', ['q0', 'q1', 'q2', 'q3']), 7: ('rl h1', ['q0', 'q1', 'q2', 'q3']),
              1: ('mma ', ['wait_tempty', 'got_tempty', 'got_full', 'committed']),
