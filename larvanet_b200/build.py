@@ -66,7 +66,7 @@ def build(force=False, verbose=False):
             if verbose:
                 print(logs[-1])
     if jobs:
-        with open(os.path.join(BUILD, 'ptxas.log'), 'a' if not force else 'w') as f:
+        with open(os.path.join(BUILD, 'ptxas.log'), 'w') as f:
             f.write('\n'.join(logs))
     if force or jobs or not os.path.exists(LIB):
         cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']

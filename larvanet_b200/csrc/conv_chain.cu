@@ -98,8 +98,9 @@ struct FastEpi {
   int relu;
 };
 
-template <int EPI, int NT>
-__device__ __forceinline__ void fast_tile(const FastEpi& e, const float* breg, bool valid, size_t o0, size_t chunk_stride,
+template <int EPI, int NT, bool BIAS_REGS>
+__device__ __forceinline__ void fast_tile(const FastEpi& e, const float* breg, const float* bias_g, bool valid, size_t o0,
+                                          size_t chunk_stride,
                                           uint32_t taddr, uint32_t tfull, uint32_t tempty, uint32_t parity) {
   constexpr int NCH = NT / 8;
   const bool unit_scale = (EPI >= 0) || (e.res_scale == 1.0f);
@@ -135,8 +136,15 @@ __device__ __forceinline__ void fast_tile(const FastEpi& e, const float* breg, b
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       float* vj = v + 8 * j;
+      if constexpr (BIAS_REGS) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) vj[i] += breg[8 * j + i];
+        for (int i = 0; i < 8; ++i) vj[i] += breg[8 * j + i];
+      } else if (bias_g != nullptr) {   // L1-resident after the first tile
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias_g) + 2 * j);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias_g) + 2 * j + 1);
+        vj[0] += b0.x; vj[1] += b0.y; vj[2] += b0.z; vj[3] += b0.w;
+        vj[4] += b1.x; vj[5] += b1.y; vj[6] += b1.z; vj[7] += b1.w;
+      }
       if (!unit_scale) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) vj[i] *= e.res_scale;
@@ -166,6 +174,171 @@ __device__ __forceinline__ void fast_tile(const FastEpi& e, const float* breg, b
       store8(po + j * chunk_stride, vj);
     }
   }
+}
+
+// PixelShuffle(4) + bicubic base (+ L1 loss / sign gradient) epilogue of one tile for one thread, same arithmetic as
+// conv_epilogue16's LV_EPI_PS4_NCHW branch but software-pipelined: the base / truth lines of colour plane c+1 are in
+// flight while plane c is computed, and the first plane's are issued before the accumulator wait.
+template <int NT>
+__device__ __forceinline__ float ps4_tile(const lv_conv_args& a, const float* bias_g, bool valid, int n, int y, int x, int H,
+                                          int W, size_t o0, size_t chunk_stride, uint32_t taddr, uint32_t tfull,
+                                          uint32_t tempty, uint32_t parity) {
+  static_assert(NT == 48, "three colour planes of 16 sub-pixels");
+  const size_t W4 = static_cast<size_t>(W) * 4;
+  const size_t plane = static_cast<size_t>(H) * 4 * W4;
+  const size_t hr0 = (static_cast<size_t>(n) * 3 * (static_cast<size_t>(H) * 4) + 4 * y) * W4 + 4 * x;   // colour 0, dy 0
+  const bool has_base = a.base_hr != nullptr, has_truth = a.truth_hr != nullptr, has_out = a.out_hr != nullptr;
+  const bool has_sign = has_truth && a.grad_sign != nullptr;
+  float4 qb[4], qt[4];
+  auto load_plane = [&](int c, float4* b4, float4* t4) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const size_t off = hr0 + c * plane + i * W4;
+      b4[i] = (valid && has_base) ? __ldg(reinterpret_cast<const float4*>(a.base_hr + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      t4[i] = (valid && has_truth) ? __ldg(reinterpret_cast<const float4*>(a.truth_hr + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load_plane(0, qb, qt);
+  mbar_wait_relaxed(tfull, parity);
+  tc_fence_after_sync();
+  float loss = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[16];
+    tmem_ld16(taddr + c * 16, v);
+    float4 nb[4], nt[4];
+    if (c < 2) load_plane(c + 1, nb, nt);
+    tmem_ld_wait();
+    if (c == 2) {
+      tc_fence_before_sync();
+      mbar_arrive(tempty);
+    }
+    if (valid) {
+      float gs[16];
+      float closs = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 bb = (bias_g != nullptr) ? __ldg(reinterpret_cast<const float4*>(bias_g) + c * 4 + i)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o = make_float4(v[4 * i] + bb.x, v[4 * i + 1] + bb.y, v[4 * i + 2] + bb.z, v[4 * i + 3] + bb.w);
+        if (has_base) { o.x += qb[i].x; o.y += qb[i].y; o.z += qb[i].z; o.w += qb[i].w; }
+        if (has_out) *reinterpret_cast<float4*>(a.out_hr + hr0 + c * plane + i * W4) = o;
+        if (has_truth) {
+          const float d0 = o.x - qt[i].x, d1 = o.y - qt[i].y, d2 = o.z - qt[i].z, d3 = o.w - qt[i].w;
+          closs += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+          gs[4 * i + 0] = (d0 > 0.f) ? 1.f : ((d0 < 0.f) ? -1.f : 0.f);
+          gs[4 * i + 1] = (d1 > 0.f) ? 1.f : ((d1 < 0.f) ? -1.f : 0.f);
+          gs[4 * i + 2] = (d2 > 0.f) ? 1.f : ((d2 < 0.f) ? -1.f : 0.f);
+          gs[4 * i + 3] = (d3 > 0.f) ? 1.f : ((d3 < 0.f) ? -1.f : 0.f);
+        }
+      }
+      loss += closs;
+      if (has_sign) {
+        __nv_bfloat16* gp = reinterpret_cast<__nv_bfloat16*>(a.grad_sign) + o0 + (2 * c) * chunk_stride;
+        store8(gp, gs);
+        store8(gp + chunk_stride, gs + 8);
+      }
+    }
+    if (c < 2) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { qb[i] = nb[i]; qt[i] = nt[i]; }
+    }
+  }
+  return loss;
+}
+
+// Everything an epilogue thread needs that does not change from layer to layer.
+struct EpiCtx {
+  ConvGeom g;
+  const uint32_t* done;
+  volatile uint32_t* pub_seen;
+  uint32_t tfull, tempty, pub_bar0, taddr;   // this group's accumulator-stage barriers, publish-barrier ring, TMEM address
+  int G, H, W, tiles_per_img, r, c, lane, eg;
+  bool tl0;
+  size_t chunk_stride;
+};
+
+constexpr int kKindPs4 = 100, kKindGeneric = -1;
+
+// All tiles of one layer for one epilogue thread.  KIND: 0/1/2/4/12 = straight-line planar epilogue with that flag
+// set, kKindPs4 = PixelShuffle(4)+base(+loss), kKindGeneric = shared 16-channel routine.  The register-hungry kinds
+// (two residuals, PixelShuffle) read the bias through L1 instead of holding 48 more registers across the tile loop.
+template <int KIND, int NT>
+__device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_args& a, int l, int first, uint32_t k) {
+  constexpr int NCH = NT / 8;
+  const bool has_ops = (a.mask != nullptr) || (a.res1 != nullptr) || (a.res2 != nullptr);
+  FastEpi fe;
+  fe.mask = reinterpret_cast<const __nv_bfloat16*>(a.mask);
+  fe.res1 = reinterpret_cast<const __nv_bfloat16*>(a.res1);
+  fe.res2 = reinterpret_cast<const __nv_bfloat16*>(a.res2);
+  fe.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  fe.res_scale = a.res_scale;
+  fe.relu = a.relu;
+  float loss = 0.f;
+  constexpr bool kBiasRegs = (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 4);
+  float breg[kBiasRegs ? NT : 1];
+  const float* bias_g = a.bias;
+  if constexpr (kBiasRegs) {
+#pragma unroll
+    for (int i = 0; i < NT / 4; ++i) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + i);
+      breg[4 * i] = b4.x; breg[4 * i + 1] = b4.y; breg[4 * i + 2] = b4.z; breg[4 * i + 3] = b4.w;
+    }
+  }
+  for (int tile = first; tile < cx.g.total_tiles; tile += cx.G, ++k) {
+    if ((k & 1u) != static_cast<uint32_t>(cx.eg)) continue;
+    const int n = tile / cx.tiles_per_img;
+    const int rem = tile - n * cx.tiles_per_img;
+    const int tyi = rem / cx.g.tiles_x;
+    const int y = tyi * kTileH + cx.r, x = (rem - tyi * cx.g.tiles_x) * kTileW + cx.c;
+    const bool valid = (y < cx.H) && (x < cx.W);
+    const size_t o0 = valid ? act_off(n, y, x, 0, cx.H, cx.W, NCH) : 0;
+    // pub_bar ring safety: the publisher must have seen this barrier's previous use (job k-4); read the counter now,
+    // test it after the stores
+    const uint32_t seen = *cx.pub_seen;
+    if (l > 0 && (KIND == kKindGeneric || has_ops)) {
+      // same-tile operands come from earlier layers of this chain, possibly written by another CTA
+      if (cx.lane == 0) wait_flag(cx.done + tile, kWarpsPerTile * static_cast<uint32_t>(l));
+      __syncwarp();
+    }
+    if (cx.tl0) tl_stamp(cx.g, 2, k, 0);
+    const uint32_t par = (k >> 1) & 1;
+    if constexpr (KIND == kKindPs4) {
+      loss += ps4_tile<NT>(a, bias_g, valid, n, y, x, cx.H, cx.W, o0, cx.chunk_stride, cx.taddr, cx.tfull, cx.tempty, par);
+    } else if constexpr (KIND == kKindGeneric) {
+      mbar_wait_relaxed(cx.tfull, par);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int j = 0; j < NT / 16; ++j) {
+        float v[16];
+        tmem_ld16(cx.taddr + j * 16, v);
+        tmem_ld_wait();
+        if (valid) loss += conv_epilogue16<__nv_bfloat16>(a, n, y, x, j * 16, v);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(cx.tempty);
+    } else {
+      fast_tile<KIND, NT, kBiasRegs>(fe, breg, bias_g, valid, o0, cx.chunk_stride, cx.taddr, cx.tfull, cx.tempty, par);
+    }
+    // this warp's quarter of (layer l, tile) is on its way to global memory: hand it to the publisher warp
+    __syncwarp();
+    if (cx.lane == 0) {
+      if (k >= 4 && seen + 3u < k) {
+        uint32_t spins = 0;
+        while (*cx.pub_seen + 3u < k) {
+          if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+        }
+      }
+      mbar_arrive(cx.pub_bar0 + 8u * (k & 3u));
+    }
+    if (cx.tl0) tl_stamp(cx.g, 2, k, 3);
+  }
+  if (a.truth_hr != nullptr && a.loss_sum != nullptr) {
+    loss = warp_sum(loss);
+    if (cx.lane == 0) atomicAdd(a.loss_sum, static_cast<double>(loss));
+  }
+  return k;
 }
 
 template <int CIN, int NT, int NSTAGE>
@@ -374,99 +547,50 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
     __syncwarp();
   } else {
     // =============================== epilogue: TMEM -> registers -> global ========================
-    const int eg = warp >> 2, q = warp & 3;
+    EpiCtx cx;
+    cx.eg = warp >> 2;
+    const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int r = m >> 3, c = m & 7;
-    const bool tl0 = (q == 0 && lane == 0);
-    const uint32_t as = eg;
-    constexpr int NCH = NT / 8;
-    const size_t chunk_stride = static_cast<size_t>(W) * 8;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C_::ACC_STRIDE;
+    cx.r = m >> 3;
+    cx.c = m & 7;
+    cx.lane = lane;
+    cx.tl0 = (q == 0 && lane == 0);
+    cx.g = g;
+    cx.done = done;
+    cx.pub_seen = pub_seen;
+    cx.tfull = tfull_bar(cx.eg);
+    cx.tempty = tempty_bar(cx.eg);
+    cx.pub_bar0 = pub_bar(0);
+    cx.taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cx.eg * C_::ACC_STRIDE;
+    cx.G = G;
+    cx.H = H;
+    cx.W = W;
+    cx.tiles_per_img = tiles_per_img;
+    cx.chunk_stride = static_cast<size_t>(W) * 8;
 
     pdl_wait();
     uint32_t k = 0;   // CTA-local job counter; this group handles the jobs with k % 2 == eg
     for (int l = 0; l < nlayers; ++l) {
       const lv_conv_args& a = P.layer[l];
-      const bool fast = (a.epilogue == LV_EPI_NHWC) && (a.cout == NT);
       const bool has_ops = (a.mask != nullptr) || (a.res1 != nullptr) || (a.res2 != nullptr);
-      FastEpi fe;
-      fe.mask = reinterpret_cast<const __nv_bfloat16*>(a.mask);
-      fe.res1 = reinterpret_cast<const __nv_bfloat16*>(a.res1);
-      fe.res2 = reinterpret_cast<const __nv_bfloat16*>(a.res2);
-      fe.out = reinterpret_cast<__nv_bfloat16*>(a.out);
-      fe.res_scale = a.res_scale;
-      fe.relu = a.relu;
-      // straight-line epilogues for the flag sets LarvaNet's graphs use; anything else reads the flags at run time
-      int epi = -1;
-      if (fast && a.res_scale == 1.0f) {
-        const int code = (a.relu ? 1 : 0) | (a.mask ? 2 : 0) | (a.res1 ? 4 : 0) | (a.res2 ? 8 : 0);
-        if (code == 0 || code == 1 || code == 2 || code == 4 || code == 12) epi = code;
-      }
-      float loss = 0.f;
-      float breg[NT];
-#pragma unroll
-      for (int i = 0; i < NT / 4; ++i) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + i);
-        breg[4 * i] = b4.x; breg[4 * i + 1] = b4.y; breg[4 * i + 2] = b4.z; breg[4 * i + 3] = b4.w;
-      }
-      for (int tile = first_tile(l); tile < g.total_tiles; tile += G, ++k) {
-        if ((k & 1u) != static_cast<uint32_t>(eg)) continue;
-        const int n = tile / tiles_per_img;
-        const int rem = tile - n * tiles_per_img;
-        const int tyi = rem / g.tiles_x;
-        const int y = tyi * kTileH + r, x = (rem - tyi * g.tiles_x) * kTileW + c;
-        const bool valid = (y < H) && (x < W);
-        const size_t o0 = valid ? act_off(n, y, x, 0, H, W, NCH) : 0;
-        // pub_bar ring safety: the publisher must have seen this barrier's previous use (job k-4); read the counter
-        // now, test it after the stores
-        const uint32_t seen = *pub_seen;
-        if (l > 0 && (epi < 0 || has_ops)) {
-          // same-tile operands come from earlier layers of this chain, possibly written by another CTA
-          if (lane == 0) wait_flag(done + tile, kWarpsPerTile * static_cast<uint32_t>(l));
-          __syncwarp();
+      int kind = kKindGeneric;
+      if (a.cout == NT && a.res_scale == 1.0f) {
+        if (a.epilogue == LV_EPI_NHWC) {
+          const int code = (a.relu ? 1 : 0) | (a.mask ? 2 : 0) | (a.res1 ? 4 : 0) | (a.res2 ? 8 : 0);
+          if (code == 0 || code == 1 || code == 2 || code == 4 || code == 12) kind = code;
+        } else if (a.epilogue == LV_EPI_PS4_NCHW && !a.relu && !has_ops) {
+          kind = kKindPs4;
         }
-        if (tl0) tl_stamp(g, 2, k, 0);
-        const uint32_t par = (k >> 1) & 1;
-        if (epi >= 0) {
-          switch (epi) {
-            case 0: fast_tile<0, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
-            case 1: fast_tile<1, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
-            case 2: fast_tile<2, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
-            case 4: fast_tile<4, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
-            case 12: fast_tile<12, NT>(fe, breg, valid, o0, chunk_stride, taddr, tfull_bar(as), tempty_bar(as), par); break;
-            default: break;
-          }
-        } else {
-          // PixelShuffle and unusual flag sets: shared 16-channel routine
-          mbar_wait_relaxed(tfull_bar(as), par);
-          tc_fence_after_sync();
-#pragma unroll 1
-          for (int j = 0; j < NT / 16; ++j) {
-            float v[16];
-            tmem_ld16(taddr + j * 16, v);
-            tmem_ld_wait();
-            if (valid) loss += conv_epilogue16<__nv_bfloat16>(a, n, y, x, j * 16, v);
-          }
-          tc_fence_before_sync();
-          mbar_arrive(tempty_bar(as));
-        }
-        // this warp's quarter of (layer l, tile) is on its way to global memory: hand it to the publisher warp
-        __syncwarp();
-        if (lane == 0) {
-          if (k >= 4 && seen + 3u < k) {
-            uint32_t spins = 0;
-            while (*pub_seen + 3u < k) {
-              if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
-            }
-          }
-          mbar_arrive(pub_bar(k & 3u));
-        }
-        if (tl0) tl_stamp(g, 2, k, 3);
       }
-      if (a.truth_hr != nullptr && a.loss_sum != nullptr) {
-        loss = warp_sum(loss);
-        if (lane == 0) atomicAdd(a.loss_sum, static_cast<double>(loss));
+      const int first = first_tile(l);
+      switch (kind) {
+        case 0: k = run_layer<0, NT>(cx, a, l, first, k); break;
+        case 1: k = run_layer<1, NT>(cx, a, l, first, k); break;
+        case 2: k = run_layer<2, NT>(cx, a, l, first, k); break;
+        case 4: k = run_layer<4, NT>(cx, a, l, first, k); break;
+        case 12: k = run_layer<12, NT>(cx, a, l, first, k); break;
+        case kKindPs4: k = run_layer<kKindPs4, NT>(cx, a, l, first, k); break;
+        default: k = run_layer<kKindGeneric, NT>(cx, a, l, first, k); break;
       }
     }
   }
