@@ -242,10 +242,20 @@ def run_ours(a):
     # ---- e2e through the plugin API with host batches
     args_ns = types.SimpleNamespace(train_path='/tmp')
 
+    # host batches go through the framework's input prefetcher (pinned host -> device on a copy stream, one batch
+    # ahead), exactly as train_larva.py feeds the plugin; every step's copy is inside the timed region
+    from larvanet_b200.prefetch import DevicePrefetcher
+
+    def host_batches():
+        i = 0
+        while True:
+            yield host_pool[i % POOL]
+            i += 1
+
+    feeder = DevicePrefetcher(host_batches(), dev, depth=2)
+
     def step_e2e(i):
-        xh, th = host_pool[i % POOL]
-        x = xh.to(dev, non_blocking=True)
-        t = th.to(dev, non_blocking=True)
+        x, t = next(feeder)
         return model.train_step_larva(args_ns, None, x, t)   # returns loss.item(): D2H every step
 
     ms_e2e = timed(step_e2e, a.steps, warm)

@@ -171,14 +171,16 @@ class LarvaEngine:
                 items_b.append(dict(w=w, packed=self._pk[(prefix, 'bwd', s)], transpose=1, i_off=C * s, i_cnt=C, cin=C,
                                     dtype=dt))
         self._pack_items_fwd, self._pack_items_bwd = items_f, items_b
+        # marshalled once: re-packing runs every optimizer step and must not cost host time per layer
+        self._pack_arr_fwd = ops.build_pack_arrays(items_f)
+        self._pack_arr_all = ops.build_pack_arrays(items_f + items_b)
 
     def repack(self, backward=False, force=False):
         """Refresh the packed bf16/fp32 conv operands from the fp32 master weights when they changed."""
         ver = self.arena.version()
         if not force and ver == self._packed_version and (self._packed_bwd or not backward):
             return
-        items = self._pack_items_fwd + (self._pack_items_bwd if backward else [])
-        ops.pack_weights(items)
+        ops.pack_weights_prebuilt(self._pack_arr_all if backward else self._pack_arr_fwd)
         self._packed_version = ver
         self._packed_bwd = backward
 

@@ -68,9 +68,11 @@ def packed_weight_bytes(cout, cin_total, dt):
     return int(_lib.load().lv_packed_weight_bytes(cout, cin_total, dtype_id(dt)))
 
 
-def pack_weights(items):
-    """items: list of dicts(w=fp32 OIHW tensor, packed=uint8/any tensor, transpose, i_off, i_cnt, cin, dtype)."""
-    lib = _lib.load()
+def build_pack_arrays(items):
+    """Marshal pack items once: list of (ctypes PackItem array, count) chunks of <= 64 (the C-ABI's per-call limit).
+    items: list of dicts(w=fp32 OIHW tensor, packed=uint8/any tensor, transpose, i_off, i_cnt, cin, dtype, wlayout).
+    The tensors must stay alive (and keep their storage) for as long as the arrays are used."""
+    out = []
     for start in range(0, len(items), 64):
         chunk = items[start:start + 64]
         arr = (PackItem * len(chunk))()
@@ -87,7 +89,18 @@ def pack_weights(items):
             arr[k].cin = int(it['cin'])
             arr[k].dtype = dtype_id(it['dtype'])
             arr[k].wlayout = int(it.get('wlayout', 0))
-        check(lib.lv_pack_conv3x3_weights(arr, len(chunk), _stream()), 'lv_pack_conv3x3_weights')
+        out.append((arr, len(chunk)))
+    return out
+
+
+def pack_weights_prebuilt(arrays):
+    lib = _lib.load()
+    for arr, cnt in arrays:
+        check(lib.lv_pack_conv3x3_weights(arr, cnt, _stream()), 'lv_pack_conv3x3_weights')
+
+
+def pack_weights(items):
+    pack_weights_prebuilt(build_pack_arrays(items))
 
 
 def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res1=None, res2=None, out=None,

@@ -88,22 +88,31 @@ def main(argv=None, epoch_bookkeeping=False):
     print(f'volume {model.volume_per_step/1e6:.2f}M for 1 step.')
     print(f'needs {model_args.val_volume/model.volume_per_step:.0f}steps to validate for {model_args.val_volume/1e9:.1f}G volume.')
     loss = float('nan')
+    import numpy as np
+    from larvanet_b200.prefetch import DevicePrefetcher
+
+    def host_batches():
+        # same loader calls as the reference loop (train_larva.py:112-121 there); batches are staged in pinned memory
+        while True:
+            sc = model.get_next_train_scale()
+            if dataloader.is_threaded:
+                input_list, truth_list = dataloader.get_queue_data(scale=sc)
+            else:
+                input_list, truth_list = dataloader.get_patch_batch(batch_size=args.batch_size, scale=sc,
+                                                                    input_patch_size=args.input_patch_size)
+            yield (torch.from_numpy(np.asarray(input_list, dtype=np.float32)).pin_memory(),
+                   torch.from_numpy(np.asarray(truth_list, dtype=np.float32)).pin_memory())
+
+    feeder = DevicePrefetcher(host_batches(), model.device, depth=2)
     try:
         while model.global_step < args.max_steps:
             scale = model.get_next_train_scale()
             summary = summary_writers[scale] if (model.global_step % args.summary_freq == 0) else None
             start_time = time.time()
-            if dataloader.is_threaded:
-                input_list, truth_list = dataloader.get_queue_data(scale=scale)
-            else:
-                input_list, truth_list = dataloader.get_patch_batch(batch_size=args.batch_size, scale=scale,
-                                                                    input_patch_size=args.input_patch_size)
+            # the next batch's host->device copy was issued on the copy stream while the previous step computed
+            input_tensor, truth_tensor = next(feeder)
             dataload_time = time.time() - start_time
-            check_time = time.time()
-            import numpy as np
-            input_tensor = torch.as_tensor(np.asarray(input_list), dtype=torch.float32, device=model.device)
-            truth_tensor = torch.as_tensor(np.asarray(truth_list), dtype=torch.float32, device=model.device)
-            np2ts_time = time.time() - check_time
+            np2ts_time = 0.0
             check_time = time.time()
             loss = model.train_step_larva(args=args, val_dataloader=val_dataloader, input_tensor=input_tensor,
                                           truth_tensor=truth_tensor, summary=summary)
