@@ -188,25 +188,38 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
   }
 }
 
-// workspace [item][split][col 440][co 64] -> dw / db (+=)
+// workspace [item][split][col 440][co 64] -> dw / db (+=).  One block per (item, group of 8 output channels): the
+// split sums are read as 32-byte runs of 8 channels per column, permuted through shared memory from the accumulator's
+// (tap, ci) column order to OIHW's (ci, tap), and added to dw as 432 contiguous floats per output channel.
+constexpr int kRedCo = 8;
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const lv_wgrad_item* __restrict__ items, const float* __restrict__ workspace, int splits) {
+  __shared__ float sm[kRedCo][9 * kWCin + 1];
   const lv_wgrad_item it = items[blockIdx.y];
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  const int col = idx / 64, co = idx % 64;
-  if (col >= kWCols - 7 || co >= it.cout) return;   // only the first bias column is meaningful
-  const float* ws = workspace + static_cast<size_t>(blockIdx.y) * splits * (static_cast<size_t>(kWCols) * 64) +
-                    static_cast<size_t>(col) * 64 + co;
-  float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += ws[static_cast<size_t>(k) * kWCols * 64];
-  s *= it.scale;
-  if (col < 9 * kWCin) {
-    const int tap = col / kWCin, ci = col % kWCin;
-    float* p = it.dw + (static_cast<size_t>(co) * it.cin_total + it.cin_off + ci) * 9 + tap;
-    *p += s;
-  } else if (it.db != nullptr) {
-    it.db[co] += s;
+  const int co0 = blockIdx.x * kRedCo;
+  if (co0 >= it.cout) return;
+  const float* ws0 = workspace + static_cast<size_t>(blockIdx.y) * splits * (static_cast<size_t>(kWCols) * 64);
+  constexpr int kCols = 9 * kWCin + 1;   // 432 weight columns + the first bias column
+  for (int idx = threadIdx.x; idx < kCols * kRedCo; idx += 256) {
+    const int col = idx / kRedCo, c = idx % kRedCo;
+    const float* ws = ws0 + static_cast<size_t>(col) * 64 + co0 + c;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[static_cast<size_t>(k) * kWCols * 64];   // fixed order: deterministic
+    s *= it.scale;
+    // column (tap, ci) -> OIHW offset ci*9 + tap inside the channel's row; the bias column keeps index 432
+    const int dst = (col < 9 * kWCin) ? (col % kWCin) * 9 + col / kWCin : col;
+    sm[c][dst] = s;
   }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 9 * kWCin * kRedCo; idx += 256) {
+    const int c = idx / (9 * kWCin), j = idx % (9 * kWCin);
+    const int co = co0 + c;
+    if (co < it.cout) {
+      float* p = it.dw + (static_cast<size_t>(co) * it.cin_total + it.cin_off) * 9 + j;
+      *p += sm[c][j];
+    }
+  }
+  if (threadIdx.x < kRedCo && it.db != nullptr && co0 + threadIdx.x < it.cout) it.db[co0 + threadIdx.x] += sm[threadIdx.x][9 * kWCin];
 }
 
 // ============================================================================================
@@ -355,7 +368,7 @@ int wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int c
   }
   wgrad_tc_kernel<<<dim3(splits, count), kWThreads, kWSmem, stream>>>(items_dev, static_cast<float*>(workspace), splits);
   LV_LAUNCH_OK();
-  wgrad_reduce_kernel<<<dim3((kWCols * 64 + 255) / 256, count), 256, 0, stream>>>(items_dev, static_cast<const float*>(workspace),
+  wgrad_reduce_kernel<<<dim3(64 / kRedCo, count), 256, 0, stream>>>(items_dev, static_cast<const float*>(workspace),
                                                                                   splits);
   LV_LAUNCH_OK();
   return LV_OK;
