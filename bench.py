@@ -291,7 +291,11 @@ def run_ours(a):
         ach = float(fl.sum() / durs.sum() / 1e12)
         peak = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
         line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                            'traffic': None, 'kernel': 'conv3x3_chain_kernel<48,48> (forward and backward-data conv chains, one persistent launch each)',
+                            # dram__bytes_read.sum + dram__bytes_write.sum of the step's 80 chained layers from the
+                            # ncu --set full capture in profiles/r01c_conv_chain_ncu_full_summary.txt (two launches
+                            # there: 64 + 16 layers), per training step; algorithmic: 80 x 3.54 MB of saved activations
+                            'traffic': 320.1e6 / max(1, len(recs)),
+                            'kernel': 'conv3x3_chain_kernel<48,48> (forward + backward-data conv layers of the step, persistent data-flow launch)',
                             'launches_timed': len(recs), 'avg_launch_us': float(durs.mean() * 1e6),
                             'peak_source': peaks_src + ', sustained bf16 (kernel timed inside a long step)'}
         line['clocks'] = clocks

@@ -10,7 +10,10 @@
  *   - all pointers are DEVICE pointers unless a parameter says "host"; the library never allocates, frees or
  *     synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).
  *   - return value: 0 = ok, otherwise an LV_ERR_* code; lv_last_error() returns a thread-local message.
- *   - activations are NHWC.  dtype LV_BF16 is the product path (tcgen05 tensor cores, fp32 accumulate);
+ *   - activations are channels-last in 8-channel planes ("planar-8"): element (n, y, x, c) of a C-channel tensor lives
+ *     at ((((n*H + y) * (C/8) + c/8) * W + x) * 8 + c%8), i.e. [N][H][C/8][W][8]; C must be a multiple of 8.  Comments
+ *     and names below that say "NHWC [n,h,w,c]" mean this layout (logical NHWC indexing, planar-8 storage).
+ *     dtype LV_BF16 is the product path (tcgen05 tensor cores, fp32 accumulate);
  *     dtype LV_F32 is the fp32 validation mode (CUDA-core direct convolution, same epilogues).
  *   - images at the Python boundary stay NCHW fp32 on the 0..255 scale like the reference
  *     (models/LarvaNet.py:163-171).
@@ -139,13 +142,14 @@ int lv_conv3x3_simt(const lv_conv_args* args, void* stream);
  * lv_conv3x3, but the CTAs stay resident and the layers are linked by per-tile data-flow flags instead of kernel
  * boundaries (no launch, prologue or pipeline drain per layer).  Replaces the Conv2d sequences of
  * models/LarvaNet.py:116-140 (ResidualBlock / LarvaBody) and :178-201 (LarvaLeg), forward and input-gradient.
- *   layers:  HOST array (copied by value into the launch), 1 <= count <= 64; every layer must be a single-source
+ *   layers:  HOST array (copied by value into the launch), 1 <= count <= LV_CHAIN_MAX_LAYERS; every layer must be a single-source
  *            LV_BF16 48 -> 48 conv with LV_W_TAP_MAJOR weights and 16-byte aligned bias, all on the same (n, h, w).
  *            A layer may read (src / res1 / res2 / mask) anything written by an EARLIER layer of the chain or before
  *            the call, and may overwrite any buffer whose readers are earlier layers.
  *   sync_ws: device workspace of lv_conv_chain_workspace_bytes(n, h, w) bytes; zero it once after allocation, the
  *            kernel leaves it zeroed.  One workspace per stream.
  */
+#define LV_CHAIN_MAX_LAYERS 96
 int64_t lv_conv_chain_workspace_bytes(int n, int h, int w);
 int lv_conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, int64_t sync_ws_bytes, int max_ctas,
                      void* stream);

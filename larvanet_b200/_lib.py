@@ -16,6 +16,7 @@ LV_F32, LV_BF16 = 0, 1
 LV_EPI_NHWC, LV_EPI_PS4_NCHW, LV_EPI_PS2_NHWC, LV_EPI_RGB_NCHW = 0, 1, 2, 3
 LV_MAX_SRC = 4
 LV_W_TAP_MAJOR, LV_W_KY_STACKED = 0, 1
+LV_CHAIN_MAX_LAYERS = 96
 ABI_VERSION = 1
 
 

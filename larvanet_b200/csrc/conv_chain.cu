@@ -21,7 +21,7 @@
 // unfinished job can always proceed (no cyclic waits).  The last CTA to leave re-zeroes the flags, so the workspace is
 // ready for the next launch (also under CUDA-graph replay, where arguments are frozen).
 //
-// The layer descriptors travel as a kernel parameter (64 x lv_conv_args in the constant bank).
+// The layer descriptors travel as a kernel parameter (up to 96 x lv_conv_args = 17.7 KB in the constant bank).
 #include "conv_epilogue.cuh"
 #include "lv_common.cuh"
 
@@ -32,7 +32,7 @@ extern int g_use_pdl;
 
 namespace chain {
 
-constexpr int kMaxLayers = 64;
+constexpr int kMaxLayers = 96;   // LV_CHAIN_MAX_LAYERS
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2, kHaloPix = kHaloW * kHaloH;  // 10 x 18 = 180
 constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 64;

@@ -181,8 +181,8 @@ def conv3x3_chain(arg_list, workspace, max_ctas=0):
     if n == 0:
         return
     pos = 0
-    while pos < n:   # the C-ABI takes at most 64 layers per launch
-        cnt = min(64, n - pos)
+    while pos < n:   # the C-ABI takes at most LV_CHAIN_MAX_LAYERS layers per launch
+        cnt = min(_lib.LV_CHAIN_MAX_LAYERS, n - pos)
         arr = (_lib.ConvArgs * cnt)(*arg_list[pos:pos + cnt])
         if CONV_TIMERS is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
