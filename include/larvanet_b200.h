@@ -187,6 +187,19 @@ int lv_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w_, in
 int lv_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w_, int dtype, void* stream);
 
 /*
+ * uint8 image helpers on fp32 0..255 images (any layout, element-wise):
+ *   lv_image_to_uint8: dst = clip(round_half_even(src), 0, 255)       (validate._image_to_uint8, validate.py:17-18;
+ *                      get_sr.py:86-89 before the PNG is written) -- 4x less device->host traffic than the fp32 image.
+ *   lv_psnr_sqsum:     *sq_sum += sum over [c, h, w] of (u8(truth) - u8(out))^2, truth [c, truth_h, truth_w] cropped to
+ *                      the output's [c, h, w] (validate._fit_truth_image_size + _image_psnr, validate.py:20-27);
+ *                      PSNR = 10*log10(255^2 * c*h*w / sq_sum).  Lets LarvaNet.validate_for_train (models/LarvaNet.py:
+ *                      141-161) score on the device and read back 8 bytes per image.
+ */
+int lv_image_to_uint8(const float* src, uint8_t* dst, int64_t numel, void* stream);
+int lv_psnr_sqsum(const float* out, const float* truth, double* sq_sum, int c, int h, int w_, int truth_h, int truth_w,
+                  void* stream);
+
+/*
  * Stand-alone L1 loss + gradient on fp32 NCHW HR images (nn.L1Loss, models/LarvaNet.py:85,108):
  *   loss_sum += sum|out-truth|;  if grad_sign: sign(out-truth) un-shuffled (PixelShuffle(4) backward) to
  *   NHWC [n,h,w,16*c] of dtype.

@@ -77,6 +77,8 @@ SIGNATURES = {
     'lv_conv3x3_wgrad_simt': (C.c_int, [C.POINTER(WgradItem), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'lv_nchw_to_nhwc': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'lv_nhwc_to_nchw': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'lv_image_to_uint8': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'lv_psnr_sqsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'lv_l1_loss_grad': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
     'lv_adamw_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_void_p]),
     'lv_launch_count': (C.c_int64, []),

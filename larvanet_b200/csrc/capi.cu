@@ -52,6 +52,8 @@ int nchw_to_nhwc(const float*, void*, int, int, int, int, int, cudaStream_t);
 int nhwc_to_nchw(const void*, float*, int, int, int, int, int, cudaStream_t);
 int l1_loss_grad(const float*, const float*, double*, void*, int, int, int, int, int, cudaStream_t);
 int adamw_step(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
+int image_to_uint8(const float*, uint8_t*, long long, cudaStream_t);
+int psnr_sqsum(const float*, const float*, double*, int, int, int, int, int, cudaStream_t);
 long long wgrad_workspace_bytes(const lv_wgrad_item*, int, int);
 int wgrad(const lv_wgrad_item*, const lv_wgrad_item*, int, int, void*, cudaStream_t);
 int wgrad_simt(const lv_wgrad_item*, const lv_wgrad_item*, int, int, cudaStream_t);
@@ -209,6 +211,18 @@ int lv_l1_loss_grad(const float* out_hr, const float* truth_hr, double* loss_sum
                     int w_, int dtype, void* stream) {
   LV_CHECK_ARG(out_hr && truth_hr, "l1: null pointer");
   return l1_loss_grad(out_hr, truth_hr, loss_sum, grad_sign, n, c, h, w_, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int lv_image_to_uint8(const float* src, uint8_t* dst, int64_t numel, void* stream) {
+  LV_CHECK_ARG(numel >= 0 && (numel == 0 || (src && dst)), "image_to_uint8: null pointer");
+  return image_to_uint8(src, dst, numel, static_cast<cudaStream_t>(stream));
+}
+
+int lv_psnr_sqsum(const float* out, const float* truth, double* sq_sum, int c, int h, int w_, int truth_h, int truth_w,
+                  void* stream) {
+  LV_CHECK_ARG(out && truth && sq_sum, "psnr: null pointer");
+  LV_CHECK_ARG(c >= 0 && h >= 0 && w_ >= 0, "psnr: negative size");
+  return psnr_sqsum(out, truth, sq_sum, c, h, w_, truth_h, truth_w, static_cast<cudaStream_t>(stream));
 }
 
 int lv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1,

@@ -211,6 +211,67 @@ int l1_loss_grad(const float* out_hr, const float* truth_hr, double* loss_sum, v
 }
 
 // ---------------------------------------------------------------------------------------------
+// uint8 image helpers (validate._image_to_uint8 / _image_psnr, reference validate.py:17-27): np.round is
+// round-half-to-even == __float2int_rn; then clip to 0..255.
+__device__ __forceinline__ int to_u8(float v) {
+  const int r = __float2int_rn(v);
+  return r < 0 ? 0 : (r > 255 ? 255 : r);
+}
+
+__global__ void __launch_bounds__(256)
+image_to_uint8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, long long total) {
+  // four pixels per thread: one 16 B load, one 4 B store
+  const long long quads = total / 4;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < quads; i += static_cast<long long>(gridDim.x) * 256) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    uchar4 o;
+    o.x = static_cast<unsigned char>(to_u8(v.x)); o.y = static_cast<unsigned char>(to_u8(v.y));
+    o.z = static_cast<unsigned char>(to_u8(v.z)); o.w = static_cast<unsigned char>(to_u8(v.w));
+    reinterpret_cast<uchar4*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < static_cast<int>(total - quads * 4)) {
+    const long long i = quads * 4 + threadIdx.x;
+    dst[i] = static_cast<unsigned char>(to_u8(src[i]));
+  }
+}
+
+int image_to_uint8(const float* src, uint8_t* dst, long long total, cudaStream_t stream) {
+  if (total == 0) return LV_OK;
+  LV_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 3u) == 0,
+               "image_to_uint8: src must be 16-byte and dst 4-byte aligned");
+  image_to_uint8_kernel<<<grid_for((total + 3) / 4), 256, 0, stream>>>(src, dst, total);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+// sum over (c, y < h, x < w) of (u8(truth[c][y][x]) - u8(out[c][y][x]))^2, truth cropped to the output's size
+// (validate._fit_truth_image_size); exact in integers, accumulated as double
+__global__ void __launch_bounds__(256)
+psnr_sqsum_kernel(const float* __restrict__ out, const float* __restrict__ truth, double* __restrict__ sq_sum, int c, int h,
+                  int w, int th, int tw) {
+  const long long total = static_cast<long long>(c) * h * w;
+  unsigned long long acc = 0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * 256) {
+    const int x = static_cast<int>(i % w);
+    const int y = static_cast<int>((i / w) % h);
+    const int ch = static_cast<int>(i / (static_cast<long long>(w) * h));
+    const int d = to_u8(truth[(static_cast<long long>(ch) * th + y) * tw + x]) - to_u8(out[i]);
+    acc += static_cast<unsigned long long>(d * d);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0) atomicAdd(sq_sum, static_cast<double>(acc));
+}
+
+int psnr_sqsum(const float* out, const float* truth, double* sq_sum, int c, int h, int w, int th, int tw, cudaStream_t stream) {
+  LV_CHECK_ARG(th >= h && tw >= w, "psnr: truth (%d x %d) smaller than output (%d x %d)", th, tw, h, w);
+  const long long total = static_cast<long long>(c) * h * w;
+  if (total == 0) return LV_OK;
+  psnr_sqsum_kernel<<<grid_for(total), 256, 0, stream>>>(out, truth, sq_sum, c, h, w, th, tw);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // AdamW over a flat arena, torch.optim.AdamW semantics (decoupled weight decay, bias-corrected).
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,

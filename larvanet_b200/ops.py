@@ -275,6 +275,25 @@ def nhwc_to_nchw(src, dst):
                                       dtype_id(src.dtype), _stream()), 'lv_nhwc_to_nchw')
 
 
+def image_to_uint8(src, dst=None):
+    """clip(round(src), 0, 255) as uint8 (validate._image_to_uint8) on the device; src: fp32 CUDA tensor."""
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.uint8, device=src.device)
+    check(_lib.load().lv_image_to_uint8(_ptr(src, torch.float32, 'src'), _ptr(dst, torch.uint8, 'dst'), src.numel(),
+                                        _stream()), 'lv_image_to_uint8')
+    return dst
+
+
+def psnr_sqsum(out_chw, truth_chw, sq_sum):
+    """sq_sum (float64[1]) += sum (u8(truth) - u8(out))^2 over out's [c,h,w]; truth may be larger (cropped)."""
+    c, h, w = (int(v) for v in out_chw.shape)
+    tc, th, tw = (int(v) for v in truth_chw.shape)
+    if tc != c:
+        raise _lib.LarvaNetB200Error(f"psnr: channel mismatch {tc} vs {c}")
+    check(_lib.load().lv_psnr_sqsum(_ptr(out_chw, torch.float32, 'out'), _ptr(truth_chw, torch.float32, 'truth'),
+                                    _ptr(sq_sum, torch.float64, 'sq_sum'), c, h, w, th, tw, _stream()), 'lv_psnr_sqsum')
+
+
 def l1_loss_grad(out_hr, truth_hr, loss_sum, grad_sign=None):
     n, c, h4, w4 = (int(v) for v in out_hr.shape)
     dt = dtype_id(grad_sign.dtype) if grad_sign is not None else LV_F32

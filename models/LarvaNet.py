@@ -279,13 +279,25 @@ class LarvaNet(BaseModel):
     def validate_for_train(self, args, dataloader):
         import validate
         print('begin validation')
-        psnr_list = []
+        # Scored on the device (lv_psnr_sqsum == _image_to_uint8 + _fit_truth_image_size + _image_psnr): the truth
+        # images are uploaded once and kept, each validation reads back 8 bytes per image instead of the HR frame.
+        from larvanet_b200 import ops
+        if not hasattr(self, '_val_truth'):
+            self._val_truth = {}
+        sq_sums, numels = [], []
         for image_index in range(dataloader.get_num_images()):
             input_image, truth_image, _ = dataloader.get_image_pair(image_index=image_index, scale=4)
-            output_image = validate._image_to_uint8(self.upscale(input_list=[input_image], scale=4)[0])
-            truth_image = validate._image_to_uint8(truth_image)
-            truth_image = validate._fit_truth_image_size(output_image=output_image, truth_image=truth_image)
-            psnr_list.append(validate._image_psnr(output_image=output_image, truth_image=truth_image))
+            out = self.model(self._as_input([input_image]))[0].contiguous()
+            key = (id(dataloader), image_index)
+            if key not in self._val_truth:
+                self._val_truth[key] = torch.as_tensor(np.asarray(truth_image), dtype=torch.float32,
+                                                       device=self.device).contiguous()
+            sq = torch.zeros(1, dtype=torch.float64, device=self.device)
+            ops.psnr_sqsum(out, self._val_truth[key], sq)
+            sq_sums.append(sq)
+            numels.append(out.numel())
+        mses = torch.cat(sq_sums).cpu().numpy() / np.asarray(numels, dtype=np.float64)
+        psnr_list = 10.0 * np.log10(255.0 ** 2 / mses)
         average_psnr = np.mean(psnr_list)
         print(f'step {self.global_step}, volume {self.total_volume/1e9:.0f}G,'
               f' psnr={average_psnr:.8f}, lr = {self.get_lr():.8f}')
@@ -298,6 +310,13 @@ class LarvaNet(BaseModel):
 
     def upscale(self, input_list, scale):
         return self.model(self._as_input(input_list)).detach().cpu().numpy()
+
+    def upscale_uint8(self, input_list, scale):
+        """`validate._image_to_uint8(self.upscale(...))` with the round/clip done on the device: the device->host copy
+        is 1 byte per sample instead of 4 (what get_sr.py / validate.py need before they write or score a PNG)."""
+        from larvanet_b200 import ops
+        out = self.model(self._as_input(input_list))
+        return ops.image_to_uint8(out.contiguous()).cpu().numpy()
 
     def test(self, input_list):
         return self.model(self._as_input(input_list))

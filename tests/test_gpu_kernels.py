@@ -385,3 +385,22 @@ def test_conv_chain_rejects_bad_layers():
         ops.conv3x3_chain([L[0], bad], ws)
     with pytest.raises(_lib.LarvaNetB200Error):
         ops.conv3x3_chain(L, torch.zeros(1, dtype=torch.int32, device='cuda'))
+
+
+def test_uint8_and_psnr_helpers():
+    """lv_image_to_uint8 == validate._image_to_uint8 (round-half-even, clip), lv_psnr_sqsum == _fit_truth + _image_psnr."""
+    rs = np.random.RandomState(21)
+    img = rs.uniform(-20, 280, (3, 37, 53)).astype(np.float32)
+    img.flat[:8] = [0.5, 1.5, 2.5, 254.5, 255.5, -0.5, 127.49999, 300.0]      # ties and clip edges
+    got = ops.image_to_uint8(torch.from_numpy(img).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(got, O.image_to_uint8(img))
+    odd = rs.uniform(0, 255, 1001).astype(np.float32)                            # tail that is not a multiple of 4
+    np.testing.assert_array_equal(ops.image_to_uint8(torch.from_numpy(odd).cuda()).cpu().numpy(), O.image_to_uint8(odd))
+    truth = rs.uniform(-5, 260, (3, 40, 60)).astype(np.float32)                  # larger than the output: cropped
+    sq = torch.zeros(1, dtype=torch.float64, device='cuda')
+    ops.psnr_sqsum(torch.from_numpy(img).cuda(), torch.from_numpy(truth).cuda(), sq)
+    o8, t8 = O.image_to_uint8(img), O.image_to_uint8(truth)[:, :37, :53]
+    ref_sq = float(((t8.astype(np.int64) - o8.astype(np.int64)) ** 2).sum())
+    assert sq.item() == ref_sq
+    psnr = 10.0 * np.log10(255.0 ** 2 / (sq.item() / img.size))
+    assert abs(psnr - O.image_psnr(o8, t8)) < 1e-4

@@ -77,6 +77,8 @@ def main(argv=None):
                 if args.chop_forward:
                     output_image = image_utils.upscale_with_chop_forward(model=model, input_image=input_image, scale=scale,
                                                                          overlap_size=args.chop_overlap_size)
+                elif hasattr(model, 'upscale_uint8'):   # round/clip on the device (== _image_to_uint8 below)
+                    output_image = model.upscale_uint8(input_list=[input_image], scale=scale)[0]
                 else:
                     output_image = model.upscale(input_list=[input_image], scale=scale)[0]
                 durations.append(time.perf_counter() - start)
