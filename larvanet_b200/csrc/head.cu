@@ -185,10 +185,28 @@ head_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* 
       const int gy = y0 - 1 + r, gx = x0 - 1 + q;
       sx[c][r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[((static_cast<size_t>(n) * 3 + c) * H + gy) * W + gx] : 0.f;
     }
-    for (int i = t; i < kGH * kGW * cout; i += blockDim.x) {
-      const int p = i / cout, co = i - p * cout;
-      const int gy = y0 + p / kGW, gx = x0 + p % kGW;
-      sdy[p * cp + co] = (gy < H && gx < W) ? to_f32(dy[act_off(n, gy, gx, co >> 3, H, W, cout >> 3) + (co & 7)]) : 0.f;
+    // one 8-channel chunk (16 B in bf16) per thread and step: consecutive threads read consecutive pixels of a chunk row
+    const int chunks = cout >> 3;
+    for (int i = t; i < kGH * kGW * chunks; i += blockDim.x) {
+      const int q = i % kGW, rc = i / kGW;
+      const int ch = rc % chunks, r = rc / chunks;
+      const int gy = y0 + r, gx = x0 + q;
+      float v[8];
+      if (gy < H && gx < W) {
+        const T* src = dy + act_off(n, gy, gx, ch, H, W, chunks);
+        if constexpr (sizeof(T) == 2) {
+          load8(reinterpret_cast<const __nv_bfloat16*>(src), v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = to_f32(src[e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      }
+      float* d = &sdy[(r * kGW + q) * cp + ch * 8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = v[e];
     }
     __syncthreads();
     if (active) {
@@ -246,7 +264,10 @@ int head_wgrad(const float* x, const void* dy, float* dw, float* db, int n, int 
   LV_CHECK_ARG(cout <= 64 && cout % 2 == 0, "head wgrad: cout must be even and <= 64 (got %d)", cout);
   const long long tiles = static_cast<long long>(n) * ((w_ + kGW - 1) / kGW) * ((h + kGH - 1) / kGH);
   LV_CHECK_ARG(tiles < (1ll << 31), "head wgrad: too many tiles");
-  const unsigned grid = static_cast<unsigned>(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
+  // every block ends with one atomicAdd per output (1,344 of them): keep the grid at ~half the SMs so that the atomics
+  // (and not the tile math) do not dominate small problems
+  const long long cap = sm_count() / 2 > 0 ? sm_count() / 2 : 1;
+  const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
   const size_t smem = static_cast<size_t>(kGH * kGW) * (cout + 2) * sizeof(float);
   if (dtype == LV_F32)
     head_wgrad_kernel<float><<<grid, 288, smem, stream>>>(x, static_cast<const float*>(dy), dw, db, n, h, w_, cout, scale);
