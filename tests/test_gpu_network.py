@@ -251,3 +251,55 @@ def test_edsr_inference_matches_reference_golden(golden_dir, name, precision):
         b = eng.forward(x).clone()
         eng.simt = False
         assert (a - b).abs().max().item() <= 1e-2 * max(1.0, float(b.abs().max()))
+
+
+def test_upscale_uint8_and_device_psnr_match_host_path(golden_dir):
+    """model.upscale_uint8 == validate._image_to_uint8(model.upscale) bit for bit, and validate_for_train's device-side
+    PSNR (lv_psnr_sqsum) equals the reference's host computation (validate.py:17-27)."""
+    import validate
+    g, v2, blocks, params, lr, hr = _case(golden_dir, 'larvanet_m2_b21')
+    m = _make(False, blocks, 'bf16', training=True)
+    load_params(m.get_model(), params)
+    imgs = [lr[0], np.ascontiguousarray(lr[0][:, :13, :11])]
+    for img in imgs:
+        f = m.upscale(input_list=[img], scale=4)[0]
+        u = m.upscale_uint8(input_list=[img], scale=4)[0]
+        assert u.dtype == np.uint8
+        np.testing.assert_array_equal(u, validate._image_to_uint8(f))
+
+    class Loader:          # two images, truth larger than the output by a ragged margin (cropped like the reference)
+        def get_num_images(self):
+            return len(imgs)
+
+        def get_image_pair(self, image_index, scale):
+            x = imgs[image_index]
+            rs = np.random.RandomState(image_index)
+            t = rs.uniform(0, 255, (3, 4 * x.shape[1] + 3, 4 * x.shape[2] + 2)).astype(np.float32)
+            return x, t, f'img{image_index}'
+
+    loader = Loader()
+    ref = []
+    for i in range(2):
+        x, t, _ = loader.get_image_pair(i, 4)
+        o8 = validate._image_to_uint8(m.upscale(input_list=[x], scale=4)[0])
+        t8 = validate._fit_truth_image_size(output_image=o8, truth_image=validate._image_to_uint8(t))
+        ref.append(validate._image_psnr(output_image=o8, truth_image=t8))
+    seen = {}
+    m.scheduler = types.SimpleNamespace(step=lambda v: seen.setdefault('psnr', v))
+    m.validate_for_train(types.SimpleNamespace(), loader)
+    assert abs(seen['psnr'] - float(np.mean(ref))) < 1e-4
+
+
+def test_device_prefetcher_feeds_identical_batches():
+    """DevicePrefetcher yields the host batches unchanged and in order while copies run one batch ahead."""
+    from larvanet_b200.prefetch import DevicePrefetcher
+    rs = np.random.RandomState(3)
+    host = [(torch.from_numpy(rs.rand(4, 3, 8, 8).astype(np.float32)).pin_memory(),
+             torch.from_numpy(rs.rand(4, 3, 32, 32).astype(np.float32)).pin_memory()) for _ in range(7)]
+    got = []
+    for x, t in DevicePrefetcher(iter(host), 'cuda', depth=2):
+        got.append((x.clone(), t.clone()))        # the consumer must be done with a slot before it asks for the next
+        torch.cuda._sleep(200000)
+    assert len(got) == len(host)
+    for (x, t), (hx, ht) in zip(got, host):
+        assert torch.equal(x.cpu(), hx) and torch.equal(t.cpu(), ht)
