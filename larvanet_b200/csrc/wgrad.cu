@@ -1,15 +1,25 @@
 // Weight (and bias) gradients of the 3x3 convs:  dW[co][ci][ky][kx] = sum_px dY[px][co] * X[px + (ky-1,kx-1)][ci]
 //
-// Tensor-core path (bf16, cin == 48, cout <= 64): per 16x8 pixel tile the dY tile and the X halo tile are staged
-// channel-chunk-planar ([chunk][pixel][16 B]) exactly like conv_tc.cu; read as MN-major SWIZZLE_NONE UMMA operands
-// that same layout gives  A = dY^T (M = cout padded to 64, K = 16 pixels = two tile rows) and, for every tap, the
-// shifted view  B = X[. + tap] (N = 48, same K) -- so wgrad needs no transposes and no im2col either.  The nine tap
-// products accumulate in nine 48-column TMEM accumulators (432 of 512 columns) across ALL tiles of the CTA; a tenth
-// 8-column accumulator against an all-ones B tile yields the bias gradient.  Split-K over pixel tiles: each
-// (item, split) CTA writes its partial to a workspace, a second kernel reduces deterministically and accumulates into
-// the fp32 OIHW gradient.  Batched: one launch covers `count` layers (grid.y).
+// Tensor-core path (bf16, cin == 48, cout in {16,32,48,64}).  Per 16x8 pixel tile two TMA tensor-map boxes land in
+// shared memory:  the X halo tile {10 px, 6 chunks, 18 rows} as [row][chunk][10 px x 16 B] and the dY tile
+// {8 px, cout/8 chunks, 16 rows} as [row][chunk][8 px x 16 B]; zero padding is the TMA unit's out-of-bounds fill.
+// Read as MN-major SWIZZLE_NONE UMMA operands (K = 16 pixels = two tile rows):
+//   * B = dY:  N = cout, chunk stride 128 B, K-group (tile row) stride cout/8 * 128 B;
+//   * A = X with the vertical taps STACKED ALONG M.  Chunk-plane stride is 160 B and a halo row holds exactly 6 planes
+//     (960 B), so plane index m of the descriptor addresses (row + m/6, chunk m%6): M = 128 = 16 planes covers
+//     (ky=0, 48 ch), (ky=1, 48 ch), (ky=2, ch 0..31) of one horizontal tap kx (the descriptor start address moves by
+//     kx*16 B), and a second MMA of M = 64 starting at plane 16 the remaining (ky=2, ch 32..47).
+// An M=64 MMA costs as much as an M=128 one (~40-45 clk at N=48), so this is 6 MMAs per 16 pixels instead of 9 for the
+// nine taps (+1 against an all-ones A tile for the bias gradient).  Accumulators: D[(ky,ci)][(kx,co)] in 336 TMEM
+// columns, accumulated across ALL tiles of the CTA.  Split-K over pixel tiles: each (item, split) CTA writes its
+// partial to a workspace, a second kernel reduces deterministically into the fp32 OIHW gradient.  Batched: one launch
+// covers up to 64 layers (grid.y), descriptors travel as a kernel parameter.
 //
 // CUDA-core path (fp32 validation mode, and bf16 cross-check in tests): register-tiled direct accumulation.
+#include <cuda.h>
+
+#include <unordered_map>
+
 #include "lv_common.cuh"
 
 namespace lv {
@@ -17,20 +27,39 @@ namespace lv {
 // ============================================================================================
 // tensor-core path
 // ============================================================================================
-constexpr int kWT_H = 16, kWT_W = 8, kWHaloW = 10, kWHaloPix = 180;
-constexpr int kWCin = 48;
-constexpr int kWCols = 9 * kWCin + 8;       // 440 accumulator columns (9 taps x 48 + bias)
+constexpr int kWT_H = 16, kWT_W = 8, kWHaloW = 10, kWHaloH = 18;
+constexpr int kWCin = 48, kWCh = kWCin / 8;
 constexpr int kWStages = 3;
-constexpr int kWThreads = 288;
-constexpr int kDyPlane = 128 * 16;          // 2048 B
-constexpr int kXPlane = kWHaloPix * 16;     // 2880 B
-constexpr int kDyBytes = 8 * kDyPlane;      // reserve 8 chunk planes so M=64 never reads outside the stage
-constexpr int kXBytes = (kWCin / 8) * kXPlane;
-constexpr int kWStageBytes = kDyBytes + kXBytes;  // 16384 + 17280 = 33664
-constexpr int kWSmem = kWStages * kWStageBytes + 256 /*ones tile*/ + 256 /*barriers*/;
+constexpr int kWThreads = 192;               // 4 TMEM-drain warps, 1 MMA warp, 1 TMA loader warp
+constexpr int kWMaxItems = 64;               // tensor maps per launch (2 x 64 x 128 B kernel parameter)
+constexpr int kXPlaneStride = kWHaloW * 16;  // 160 B: next 8-channel chunk of the same halo row
+constexpr int kXRowPitch = kWCh * kXPlaneStride;   // 960 B: next halo row == 6 planes further
+constexpr int kXBytes = kWHaloH * kXRowPitch;      // 17280
+constexpr int kDyBytesMax = 16 * 8 * 128;          // 16384 (cout 64)
+constexpr int kWStageBytes = kDyBytesMax + kXBytes + 128;   // 33792 (keeps every stage 128 B aligned)
+constexpr int kOnesBytes = 2048;             // bf16 1.0 everywhere: the A tile of the bias MMA
+// the M=64 MMA's unused planes reach up to 5 rows past the X tile of the last stage
+constexpr int kWSmem = kWStages * kWStageBytes + kOnesBytes + 6 * kXRowPitch + 256 /*barriers*/;
+// accumulator columns: [kx*cout + co] from the M=128 MMAs, then the same for the M=64 MMAs, then the bias block
+constexpr int kWLanes = 128;
+__host__ __device__ constexpr int wcols(int cout) { return 7 * cout; }
+constexpr int kWColsMax = 7 * 64;            // 448 <= 512 TMEM columns
+
+struct WMaps {
+  CUtensorMap dy[kWMaxItems];   // planar-8 dY [n][h][cout/8][w][8], box {8 px, cout/8 chunks, 16 rows}
+  CUtensorMap x[kWMaxItems];    // planar-8 X  [n][h][6][w][8],      box {10 px, 6 chunks, 18 rows}
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
 
 __global__ void __launch_bounds__(kWThreads, 1)
-wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ workspace, int splits) {
+wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, const __grid_constant__ WMaps maps, float* __restrict__ workspace,
+                int splits) {
   extern __shared__ __align__(128) uint8_t smem[];
   const lv_wgrad_item it = items[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -38,10 +67,10 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
   const int tiles_x = (it.w + kWT_W - 1) / kWT_W, tiles_y = (it.h + kWT_H - 1) / kWT_H;
   const int tiles_per_img = tiles_x * tiles_y;
   const int total_tiles = it.n * tiles_per_img;
-  const int cho = it.cout / 8;
+  const int cout = it.cout, cho = cout / 8;
 
   uint8_t* sOnes = smem + kWStages * kWStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes + 6 * kXRowPitch);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kWStages + s); };
@@ -50,15 +79,13 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; ++s) {
-      mbar_init(full_bar(s), 128);
+      mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(done_bar, 1);
     mbar_fence_init();
   }
-  if (threadIdx.x < 128) {
-    reinterpret_cast<uint16_t*>(sOnes)[threadIdx.x] = 0x3F80u;  // bf16 1.0: [16 pixels][8] MN-major ones tile
-  }
+  for (int i = threadIdx.x; i < kOnesBytes / 4; i += kWThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
   if (warp == 4) tmem_alloc<512>(smem_u32(tmem_slot));
   fence_proxy_async_smem();
   tc_fence_before_sync();
@@ -67,86 +94,53 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp >= 5) {
-    // ------------------------------- producers -------------------------------
-    const int ptid = threadIdx.x - 160;
-    const __nv_bfloat16* X = reinterpret_cast<const __nv_bfloat16*>(it.x);
-    const __nv_bfloat16* DY = reinterpret_cast<const __nv_bfloat16*>(it.dy);
-    // tile-invariant piece tables: dY tile pieces first (128 px x cout/8 chunks), then X halo pieces (180 px x 6)
-    constexpr int kMaxPieces = (128 * 8 + kWHaloPix * (kWCin / 8) + 127) / 128;  // 17 for cout = 64
-    uint32_t pc_dst[kMaxPieces];
-    int pc_rel[kMaxPieces], pc_rc[kMaxPieces];
-    const int n_dy = 128 * cho, n_all = n_dy + kWHaloPix * (kWCin / 8);
-#pragma unroll
-    for (int i = 0; i < kMaxPieces; ++i) {
-      const int idx = ptid + i * 128;
-      if (idx < n_dy) {
-        const int p = idx / cho, c = idx - p * cho;
-        pc_dst[i] = c * kDyPlane + p * 16;
-        pc_rel[i] = (((p >> 3) * cho + c) * it.w + (p & 7)) * 8;
-        pc_rc[i] = ((p >> 3) << 8) | (p & 7);                       // bit 30 clear: dY piece (tile coordinates)
-      } else if (idx < n_all) {
-        const int j = idx - n_dy;
-        const int p = j / (kWCin / 8), c = j - p * (kWCin / 8);
-        const int r = p / kWHaloW, col = p - r * kWHaloW;
-        pc_dst[i] = kDyBytes + c * kXPlane + p * 16;
-        pc_rel[i] = (((r - 1) * (kWCin / 8) + c) * it.w + (col - 1)) * 8;
-        pc_rc[i] = (1 << 30) | (r << 8) | col;                      // bit 30 set: X halo piece (halo coordinates)
-      } else {
-        pc_dst[i] = 0; pc_rel[i] = 0; pc_rc[i] = -1;
+    // ------------------------------- loader: two TMA boxes per tile -------------------------------
+    if (elect_one()) {
+      const CUtensorMap* mdy = &maps.dy[blockIdx.y];
+      const CUtensorMap* mx = &maps.x[blockIdx.y];
+      const uint32_t bytes = static_cast<uint32_t>(cho) * 16u * 128u + kXBytes;
+      uint32_t fill = 0;
+      for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
+        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+        const int ty = rem / tiles_x;
+        const int y0 = ty * kWT_H, x0 = (rem - ty * tiles_x) * kWT_W;
+        const int stage = fill % kWStages;
+        mbar_wait_relaxed(empty_bar(stage), ((fill / kWStages) & 1) ^ 1);
+        const uint32_t st0 = smem_u32(smem + stage * kWStageBytes);
+        mbar_arrive_expect_tx(full_bar(stage), bytes);
+        tma_load_4d(st0, mdy, x0 * 8, 0, y0, n, full_bar(stage));
+        tma_load_4d(st0 + kDyBytesMax, mx, (x0 - 1) * 8, 0, y0 - 1, n, full_bar(stage));
       }
     }
-    uint32_t fill = 0;
-    for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
-      const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-      const int ty = rem / tiles_x;
-      const int y0 = ty * kWT_H, x0 = (rem - ty * tiles_x) * kWT_W;
-      const int stage = fill % kWStages;
-      mbar_wait_relaxed(empty_bar(stage), ((fill / kWStages) & 1) ^ 1);
-      const uint32_t st0 = smem_u32(smem + stage * kWStageBytes);
-      // planar-8 layout: element offset of (n, y0, chunk 0, x0)
-      const __nv_bfloat16* dy_org = DY + ((static_cast<long long>(n) * it.h + y0) * cho * it.w + x0) * 8;
-      const __nv_bfloat16* x_org = X + ((static_cast<long long>(n) * it.h + y0) * (kWCin / 8) * it.w + x0) * 8;
-#pragma unroll
-      for (int i = 0; i < kMaxPieces; ++i) {
-        if (pc_rc[i] >= 0) {
-          const bool isx = (pc_rc[i] >> 30) != 0;
-          const int rr = (pc_rc[i] >> 8) & 0xff, cc = pc_rc[i] & 0xff;
-          const int gy = y0 + rr - (isx ? 1 : 0), gx = x0 + cc - (isx ? 1 : 0);
-          const bool inb = (static_cast<unsigned>(gy) < static_cast<unsigned>(it.h)) &&
-                           (static_cast<unsigned>(gx) < static_cast<unsigned>(it.w));
-          const __nv_bfloat16* src = isx ? x_org : dy_org;
-          cp_async16(st0 + pc_dst[i], inb ? (src + pc_rel[i]) : X, inb ? 16u : 0u);
-        }
-      }
-      cp_async_mbar_arrive_noinc(full_bar(stage));
-    }
-    cp_async_wait<0>();
+    __syncwarp();
   } else if (warp == 4) {
     // ------------------------------- MMA issuer -------------------------------
     if (elect_one()) {
-      constexpr uint32_t idesc_w = umma_idesc_bf16(64, kWCin, 1, 1);
-      constexpr uint32_t idesc_b = umma_idesc_bf16(64, 8, 1, 1);
+      const uint32_t idesc_128 = umma_idesc_bf16(128, cout, 1, 1);
+      const uint32_t idesc_64 = umma_idesc_bf16(64, cout, 1, 1);
       const uint32_t ones_addr = smem_u32(sOnes);
+      const uint32_t dy_row = static_cast<uint32_t>(cho) * 128u;     // bytes of one dY tile row (all chunks)
       uint32_t fill = 0;
       for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
         const int stage = fill % kWStages;
         mbar_wait(full_bar(stage), (fill / kWStages) & 1);
-        fence_proxy_async_smem();   // consumer-side: cp.async (generic proxy) writes -> UMMA (async proxy) reads
         tc_fence_after_sync();
         const uint32_t dy0 = smem_u32(smem + stage * kWStageBytes);
-        const uint32_t xs0 = dy0 + kDyBytes;
+        const uint32_t xs0 = dy0 + kDyBytesMax;
 #pragma unroll 1
         for (int k8 = 0; k8 < 8; ++k8) {       // 16 pixels = tile rows 2*k8, 2*k8+1
           const uint32_t acc = (fill > 0 || k8 > 0) ? 1u : 0u;
-          const uint64_t adesc = umma_smem_desc(dy0 + (2 * k8) * 128, /*LBO: next K group*/ 128, /*SBO: next M chunk*/ kDyPlane);
+          // B = dY: N chunks 128 B apart, K groups (tile rows) one dY row apart
+          const uint64_t bdesc = umma_smem_desc(dy0 + (2 * k8) * dy_row, /*LBO: next K group*/ dy_row, /*SBO: next N chunk*/ 128);
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t b_addr = xs0 + ((2 * k8 + tap / 3) * kWHaloW + tap % 3) * 16;
-            const uint64_t bdesc = umma_smem_desc(b_addr, kWHaloW * 16, kXPlane);
-            umma_bf16(tmem_base + tap * kWCin, adesc, bdesc, idesc_w, acc);
+          for (int kx = 0; kx < 3; ++kx) {
+            // A = X: plane m -> (halo row 2*k8 + m/6, chunk m%6), pixels kx .. kx+7 of the row
+            const uint32_t a0 = xs0 + (2 * k8) * kXRowPitch + kx * 16;
+            umma_bf16(tmem_base + kx * cout, umma_smem_desc(a0, kXRowPitch, kXPlaneStride), bdesc, idesc_128, acc);
+            umma_bf16(tmem_base + (3 + kx) * cout, umma_smem_desc(a0 + 16 * kXPlaneStride, kXRowPitch, kXPlaneStride), bdesc,
+                      idesc_64, acc);
           }
-          const uint64_t odesc = umma_smem_desc(ones_addr, 128, 256);
-          umma_bf16(tmem_base + 9 * kWCin, adesc, odesc, idesc_b, acc);
+          umma_bf16(tmem_base + 6 * cout, umma_smem_desc(ones_addr, 128, 256), bdesc, idesc_64, acc);
         }
         umma_commit(empty_bar(stage));
       }
@@ -154,29 +148,24 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
     }
     __syncwarp();
   } else {
-    // ------------------------------- epilogue: TMEM -> workspace -------------------------------
+    // ------------------------------- epilogue: TMEM -> workspace [col][lane 128] -------------------------------
     mbar_wait_relaxed(done_bar, 0);
     tc_fence_after_sync();
-    // M = 64 accumulator layout: row r lives in TMEM lane 32*(r/16) + r%16
-    const int co = warp * 16 + lane;
-    const bool has = (lane < 16) && (co < it.cout);
-    float* ws = workspace + (static_cast<size_t>(blockIdx.y) * splits + split) * (static_cast<size_t>(kWCols) * 64);
+    const int ncols = wcols(cout);
+    float* ws = workspace + (static_cast<size_t>(blockIdx.y) * splits + split) * (static_cast<size_t>(kWColsMax) * kWLanes);
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     const bool any_tiles = split < total_tiles;
-#pragma unroll 1
-    for (int j = 0; j < kWCols / 8; j += 2) {   // 55 groups of 8 columns; read 16 at a time (last read covers 8)
+    const int l128 = warp * 32 + lane;
+    // columns [0, 3*cout): all 128 lanes ((ky, ci) rows of the M=128 MMAs); columns [3*cout, 7*cout): only TMEM lanes
+    // 0..15 carry data (rows 0..15 of an M=64 accumulator), i.e. warp 0
+    for (int j = 0; j < ncols; j += 16) {
+      if (j >= 3 * cout && warp != 0) break;
       float v[16];
-      if (j + 1 < kWCols / 8) {
-        tmem_ld16(taddr + j * 8, v);
-      } else {
-        tmem_ld16(taddr + (j - 1) * 8, v);      // overlap the previous 8 columns; keep the upper half
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = v[i + 8];
-      }
+      tmem_ld16(taddr + j, v);
       tmem_ld_wait();
-      const int ncol = (j + 1 < kWCols / 8) ? 16 : 8;
-      if (has) {
-        for (int i = 0; i < ncol; ++i) ws[static_cast<size_t>(j * 8 + i) * 64 + co] = any_tiles ? v[i] : 0.f;
+      if (j < 3 * cout || lane < 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) ws[static_cast<size_t>(j + i) * kWLanes + l128] = any_tiles ? v[i] : 0.f;
       }
     }
   }
@@ -188,38 +177,47 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, float* __restrict__ wor
   }
 }
 
-// workspace [item][split][col 440][co 64] -> dw / db (+=).  One block per (item, group of 8 output channels): the
-// split sums are read as 32-byte runs of 8 channels per column, permuted through shared memory from the accumulator's
-// (tap, ci) column order to OIHW's (ci, tap), and added to dw as 432 contiguous floats per output channel.
-constexpr int kRedCo = 8;
-__global__ void __launch_bounds__(256)
+// workspace [item][split][col][lane 128] -> dw / db (+=).  One block per (item, output channel): for each kx the 128
+// lanes of column kx*cout+co are contiguous, permuted through shared memory to OIHW's (ci, ky, kx) order and added to dw
+// as 432 contiguous floats.
+__global__ void __launch_bounds__(128)
 wgrad_reduce_kernel(const lv_wgrad_item* __restrict__ items, const float* __restrict__ workspace, int splits) {
-  __shared__ float sm[kRedCo][9 * kWCin + 1];
+  __shared__ float sm[9 * kWCin];
   const lv_wgrad_item it = items[blockIdx.y];
-  const int co0 = blockIdx.x * kRedCo;
-  if (co0 >= it.cout) return;
-  const float* ws0 = workspace + static_cast<size_t>(blockIdx.y) * splits * (static_cast<size_t>(kWCols) * 64);
-  constexpr int kCols = 9 * kWCin + 1;   // 432 weight columns + the first bias column
-  for (int idx = threadIdx.x; idx < kCols * kRedCo; idx += 256) {
-    const int col = idx / kRedCo, c = idx % kRedCo;
-    const float* ws = ws0 + static_cast<size_t>(col) * 64 + co0 + c;
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += ws[static_cast<size_t>(k) * kWCols * 64];   // fixed order: deterministic
-    s *= it.scale;
-    // column (tap, ci) -> OIHW offset ci*9 + tap inside the channel's row; the bias column keeps index 432
-    const int dst = (col < 9 * kWCin) ? (col % kWCin) * 9 + col / kWCin : col;
-    sm[c][dst] = s;
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < 9 * kWCin * kRedCo; idx += 256) {
-    const int c = idx / (9 * kWCin), j = idx % (9 * kWCin);
-    const int co = co0 + c;
-    if (co < it.cout) {
-      float* p = it.dw + (static_cast<size_t>(co) * it.cin_total + it.cin_off) * 9 + j;
-      *p += sm[c][j];
+  const int co = blockIdx.x;
+  if (co >= it.cout) return;
+  const int cout = it.cout;
+  const size_t slot = static_cast<size_t>(kWColsMax) * kWLanes;
+  const float* ws0 = workspace + static_cast<size_t>(blockIdx.y) * splits * slot;
+  const int t = threadIdx.x;
+  // rows t = ky*48 + ci of the M=128 accumulators (ky 0, 1 and ky 2 / ci < 32)
+  {
+    const int ky = t / kWCin, ci = t % kWCin;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const float* p = ws0 + static_cast<size_t>(kx * cout + co) * kWLanes + t;
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += p[k * slot];   // fixed order: deterministic
+      sm[ci * 9 + ky * 3 + kx] = s * it.scale;
     }
   }
-  if (threadIdx.x < kRedCo && it.db != nullptr && co0 + threadIdx.x < it.cout) it.db[co0 + threadIdx.x] += sm[threadIdx.x][9 * kWCin];
+  // rows 0..15 of the M=64 accumulators: ky 2, ci 32..47
+  if (t < 48) {
+    const int kx = t / 16, r = t % 16;
+    const float* p = ws0 + static_cast<size_t>((3 + kx) * cout + co) * kWLanes + r;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += p[k * slot];
+    sm[(32 + r) * 9 + 6 + kx] = s * it.scale;
+  }
+  if (t == 64 && it.db != nullptr) {
+    const float* p = ws0 + static_cast<size_t>(6 * cout + co) * kWLanes;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += p[k * slot];
+    it.db[co] += s * it.scale;
+  }
+  __syncthreads();
+  float* dst = it.dw + (static_cast<size_t>(co) * it.cin_total + it.cin_off) * 9;
+  for (int j = t; j < 9 * kWCin; j += 128) dst[j] += sm[j];
 }
 
 // ============================================================================================
@@ -318,13 +316,13 @@ static int check_items(const lv_wgrad_item* items, int count) {
 
 static bool tc_eligible(const lv_wgrad_item* items, int count) {
   for (int k = 0; k < count; ++k)
-    if (items[k].dtype != LV_BF16 || items[k].cin != kWCin || items[k].cout % 8 != 0) return false;
+    if (items[k].dtype != LV_BF16 || items[k].cin != kWCin || items[k].cout % 16 != 0 || items[k].cout > 64) return false;
   return true;
 }
 
 long long wgrad_workspace_bytes(const lv_wgrad_item* items, int count, int splits) {
   if (count <= 0 || splits <= 0 || !tc_eligible(items, count)) return 0;
-  return static_cast<long long>(count) * splits * kWCols * 64 * sizeof(float);
+  return static_cast<long long>(count) * splits * kWColsMax * kWLanes * sizeof(float);
 }
 
 int wgrad_simt(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int count, int splits, cudaStream_t stream) {
@@ -351,6 +349,62 @@ int wgrad_simt(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, 
   return LV_OK;
 }
 
+// ---- host: TMA descriptors (cached per tensor) ----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// box {`px` pixels, all chunks, `rows` rows} of a planar-8 bf16 activation tensor [n][h][chunks][w][8]
+static int tile_map(const void* src, int n, int h, int w, int chunks, int px, int rows, CUtensorMap* out) {
+  struct Key {
+    const void* p; int n, h, w, chunks, px, rows;
+    bool operator==(const Key& o) const {
+      return p == o.p && n == o.n && h == o.h && w == o.w && chunks == o.chunks && px == o.px && rows == o.rows;
+    }
+  };
+  struct Hash {
+    size_t operator()(const Key& k) const {
+      return std::hash<const void*>()(k.p) ^ (static_cast<size_t>(k.n) * 1000003u) ^ (static_cast<size_t>(k.h) << 20) ^
+             (static_cast<size_t>(k.w) << 8) ^ (static_cast<size_t>(k.chunks) << 4) ^ static_cast<size_t>(k.rows + 64 * k.px);
+    }
+  };
+  static thread_local std::unordered_map<Key, CUtensorMap, Hash> cache;
+  const Key key{src, n, h, w, chunks, px, rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return LV_OK; }
+  EncodeTiledFn enc = encode_fn();
+  LV_CHECK_ARG(enc != nullptr, "wgrad: cuTensorMapEncodeTiled is not available from this driver");
+  LV_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15u) == 0, "wgrad: activation pointers must be 16-byte aligned");
+  const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(w) * 8, static_cast<cuuint64_t>(chunks), static_cast<cuuint64_t>(h),
+                              static_cast<cuuint64_t>(n)};
+  const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(w) * 16, static_cast<cuuint64_t>(w) * 16 * chunks,
+                              static_cast<cuuint64_t>(w) * 16 * chunks * h};
+  const cuuint32_t box[4] = {static_cast<cuuint32_t>(px) * 8, static_cast<cuuint32_t>(chunks), static_cast<cuuint32_t>(rows), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LV_CHECK_ARG(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d x %d-chunk tensor",
+               static_cast<int>(r), n, h, w, chunks);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return LV_OK;
+}
+
 int wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int count, int splits, void* workspace,
           cudaStream_t stream) {
   int rc = check_items(items_host, count);
@@ -366,11 +420,23 @@ int wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int c
     LV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
     configured = true;
   }
-  wgrad_tc_kernel<<<dim3(splits, count), kWThreads, kWSmem, stream>>>(items_dev, static_cast<float*>(workspace), splits);
-  LV_LAUNCH_OK();
-  wgrad_reduce_kernel<<<dim3(64 / kRedCo, count), 256, 0, stream>>>(items_dev, static_cast<const float*>(workspace),
-                                                                                  splits);
-  LV_LAUNCH_OK();
+  static WMaps maps;   // staging only; the launch copies it by value
+  const size_t slot = static_cast<size_t>(kWColsMax) * kWLanes;
+  for (int first = 0; first < count; first += kWMaxItems) {
+    const int cnt = (count - first < kWMaxItems) ? count - first : kWMaxItems;
+    for (int k = 0; k < cnt; ++k) {
+      const lv_wgrad_item& a = items_host[first + k];
+      rc = tile_map(a.dy, a.n, a.h, a.w, a.cout / 8, kWT_W, kWT_H, &maps.dy[k]);
+      if (rc != LV_OK) return rc;
+      rc = tile_map(a.x, a.n, a.h, a.w, kWCh, kWHaloW, kWHaloH, &maps.x[k]);
+      if (rc != LV_OK) return rc;
+    }
+    float* ws = static_cast<float*>(workspace) + static_cast<size_t>(first) * splits * slot;
+    wgrad_tc_kernel<<<dim3(splits, cnt), kWThreads, kWSmem, stream>>>(items_dev + first, maps, ws, splits);
+    LV_LAUNCH_OK();
+    wgrad_reduce_kernel<<<dim3(64, cnt), 128, 0, stream>>>(items_dev + first, ws, splits);
+    LV_LAUNCH_OK();
+  }
   return LV_OK;
 }
 
