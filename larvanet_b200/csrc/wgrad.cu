@@ -11,9 +11,12 @@
 //     kx*16 B), and a second MMA of M = 64 starting at plane 16 the remaining (ky=2, ch 32..47).
 // An M=64 MMA costs as much as an M=128 one (~40-45 clk at N=48), so this is 6 MMAs per 16 pixels instead of 9 for the
 // nine taps (+1 against an all-ones A tile for the bias gradient).  Accumulators: D[(ky,ci)][(kx,co)] in 336 TMEM
-// columns, accumulated across ALL tiles of the CTA.  Split-K over pixel tiles: each (item, split) CTA writes its
-// partial to a workspace, a second kernel reduces deterministically into the fp32 OIHW gradient.  Batched: one launch
-// covers up to 64 layers (grid.y), descriptors travel as a kernel parameter.
+// columns, accumulated across the tiles of one layer.  Work split (stream-K style): the tile jobs of all layers of a launch
+// form one list that is cut into equal contiguous ranges, one per CTA (<= one CTA per SM), so every SM gets the same
+// number of tiles however many layers there are; a CTA whose range crosses a layer boundary drains its accumulators to
+// its next workspace slot and starts over.  A second kernel sums, per layer, the slots of the CTAs that touched it (fixed
+// order: deterministic) into the fp32 OIHW gradient.  Up to 64 layers per launch; descriptors and the job schedule
+// travel as kernel parameters.
 //
 // CUDA-core path (fp32 validation mode, and bf16 cross-check in tests): register-tiled direct accumulation.
 #include <cuda.h>
@@ -50,6 +53,22 @@ struct WMaps {
   CUtensorMap x[kWMaxItems];    // planar-8 X  [n][h][6][w][8],      box {10 px, 6 chunks, 18 rows}
 };
 
+struct WSched {
+  long long jobs;                 // total tile jobs of the launch
+  int count, smax;                // layers, workspace slots per CTA
+  int prefix[kWMaxItems + 1];     // first job of every layer
+  // which workspace slots hold a layer's partial sums: CTAs cta_lo .. cta_lo + ncta - 1; the layer is segment `seg0` of
+  // the first of them and segment 0 of the others (their ranges start inside the layer)
+  short cta_lo[kWMaxItems], ncta[kWMaxItems], seg0[kWMaxItems];
+};
+// first job of CTA b out of G
+__host__ __device__ inline long long wstart(long long jobs, int b, int G) { return jobs * b / G; }
+__host__ __device__ inline int witem(const WSched& sc, long long j) {
+  int i = 0;
+  while (i + 1 < sc.count && sc.prefix[i + 1] <= j) ++i;
+  return i;
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
@@ -58,24 +77,22 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
 }
 
 __global__ void __launch_bounds__(kWThreads, 1)
-wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, const __grid_constant__ WMaps maps, float* __restrict__ workspace,
-                int splits) {
+wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, const __grid_constant__ WMaps maps, const __grid_constant__ WSched sc,
+                float* __restrict__ workspace) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const lv_wgrad_item it = items[blockIdx.y];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int split = blockIdx.x;
-  const int tiles_x = (it.w + kWT_W - 1) / kWT_W, tiles_y = (it.h + kWT_H - 1) / kWT_H;
-  const int tiles_per_img = tiles_x * tiles_y;
-  const int total_tiles = it.n * tiles_per_img;
-  const int cout = it.cout, cho = cout / 8;
+  const int G = static_cast<int>(gridDim.x);
+  const long long j0 = wstart(sc.jobs, blockIdx.x, G), j1 = wstart(sc.jobs, blockIdx.x + 1, G);
+  const int item0 = witem(sc, j0);
 
   uint8_t* sOnes = smem + kWStages * kWStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + kOnesBytes + 6 * kXRowPitch);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kWStages + s); };
-  const uint32_t done_bar = bar0 + 8u * (2 * kWStages);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 1);
+  const uint32_t done_bar = bar0 + 8u * (2 * kWStages);        // MMAs of a segment retired -> drain warps
+  const uint32_t drained_bar = bar0 + 8u * (2 * kWStages + 1); // accumulators read out -> MMA warp may overwrite them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 2);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWStages; ++s) {
@@ -83,6 +100,7 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, const __grid_constant__
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(done_bar, 1);
+    mbar_init(drained_bar, 128);
     mbar_fence_init();
   }
   for (int i = threadIdx.x; i < kOnesBytes / 4; i += kWThreads) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
@@ -93,80 +111,106 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, const __grid_constant__
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  // every role walks the same segments: (layer `item`, its tiles [t0, t1)) for consecutive layers from item0
   if (warp >= 5) {
     // ------------------------------- loader: two TMA boxes per tile -------------------------------
     if (elect_one()) {
-      const CUtensorMap* mdy = &maps.dy[blockIdx.y];
-      const CUtensorMap* mx = &maps.x[blockIdx.y];
-      const uint32_t bytes = static_cast<uint32_t>(cho) * 16u * 128u + kXBytes;
       uint32_t fill = 0;
-      for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
-        const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
-        const int ty = rem / tiles_x;
-        const int y0 = ty * kWT_H, x0 = (rem - ty * tiles_x) * kWT_W;
-        const int stage = fill % kWStages;
-        mbar_wait_relaxed(empty_bar(stage), ((fill / kWStages) & 1) ^ 1);
-        const uint32_t st0 = smem_u32(smem + stage * kWStageBytes);
-        mbar_arrive_expect_tx(full_bar(stage), bytes);
-        tma_load_4d(st0, mdy, x0 * 8, 0, y0, n, full_bar(stage));
-        tma_load_4d(st0 + kDyBytesMax, mx, (x0 - 1) * 8, 0, y0 - 1, n, full_bar(stage));
+      int item = item0;
+      for (long long j = j0; j < j1; ++item) {
+        const long long seg_end = (sc.prefix[item + 1] < j1) ? sc.prefix[item + 1] : j1;
+        const lv_wgrad_item it = items[item];
+        const int tiles_x = (it.w + kWT_W - 1) / kWT_W, tiles_y = (it.h + kWT_H - 1) / kWT_H;
+        const int tiles_per_img = tiles_x * tiles_y;
+        const uint32_t bytes = static_cast<uint32_t>(it.cout / 8) * 16u * 128u + kXBytes;
+        for (int tile = static_cast<int>(j - sc.prefix[item]), t1 = static_cast<int>(seg_end - sc.prefix[item]); tile < t1;
+             ++tile, ++fill) {
+          const int n = tile / tiles_per_img, rem = tile - n * tiles_per_img;
+          const int ty = rem / tiles_x;
+          const int y0 = ty * kWT_H, x0 = (rem - ty * tiles_x) * kWT_W;
+          const int stage = fill % kWStages;
+          mbar_wait_relaxed(empty_bar(stage), ((fill / kWStages) & 1) ^ 1);
+          const uint32_t st0 = smem_u32(smem + stage * kWStageBytes);
+          mbar_arrive_expect_tx(full_bar(stage), bytes);
+          tma_load_4d(st0, &maps.dy[item], x0 * 8, 0, y0, n, full_bar(stage));
+          tma_load_4d(st0 + kDyBytesMax, &maps.x[item], (x0 - 1) * 8, 0, y0 - 1, n, full_bar(stage));
+        }
+        j = seg_end;
       }
     }
     __syncwarp();
   } else if (warp == 4) {
     // ------------------------------- MMA issuer -------------------------------
     if (elect_one()) {
-      const uint32_t idesc_128 = umma_idesc_bf16(128, cout, 1, 1);
-      const uint32_t idesc_64 = umma_idesc_bf16(64, cout, 1, 1);
       const uint32_t ones_addr = smem_u32(sOnes);
-      const uint32_t dy_row = static_cast<uint32_t>(cho) * 128u;     // bytes of one dY tile row (all chunks)
       uint32_t fill = 0;
-      for (int tile = split; tile < total_tiles; tile += splits, ++fill) {
-        const int stage = fill % kWStages;
-        mbar_wait(full_bar(stage), (fill / kWStages) & 1);
-        tc_fence_after_sync();
-        const uint32_t dy0 = smem_u32(smem + stage * kWStageBytes);
-        const uint32_t xs0 = dy0 + kDyBytesMax;
-#pragma unroll 1
-        for (int k8 = 0; k8 < 8; ++k8) {       // 16 pixels = tile rows 2*k8, 2*k8+1
-          const uint32_t acc = (fill > 0 || k8 > 0) ? 1u : 0u;
-          // B = dY: N chunks 128 B apart, K groups (tile rows) one dY row apart
-          const uint64_t bdesc = umma_smem_desc(dy0 + (2 * k8) * dy_row, /*LBO: next K group*/ dy_row, /*SBO: next N chunk*/ 128);
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            // A = X: plane m -> (halo row 2*k8 + m/6, chunk m%6), pixels kx .. kx+7 of the row
-            const uint32_t a0 = xs0 + (2 * k8) * kXRowPitch + kx * 16;
-            umma_bf16(tmem_base + kx * cout, umma_smem_desc(a0, kXRowPitch, kXPlaneStride), bdesc, idesc_128, acc);
-            umma_bf16(tmem_base + (3 + kx) * cout, umma_smem_desc(a0 + 16 * kXPlaneStride, kXRowPitch, kXPlaneStride), bdesc,
-                      idesc_64, acc);
-          }
-          umma_bf16(tmem_base + 6 * cout, umma_smem_desc(ones_addr, 128, 256), bdesc, idesc_64, acc);
+      int item = item0, seg = 0;
+      for (long long j = j0; j < j1; ++item, ++seg) {
+        const long long seg_end = (sc.prefix[item + 1] < j1) ? sc.prefix[item + 1] : j1;
+        const int cout = items[item].cout;
+        const uint32_t idesc_128 = umma_idesc_bf16(128, cout, 1, 1);
+        const uint32_t idesc_64 = umma_idesc_bf16(64, cout, 1, 1);
+        const uint32_t dy_row = static_cast<uint32_t>(cout / 8) * 128u;     // bytes of one dY tile row (all chunks)
+        if (seg > 0) {   // the previous layer's accumulators must have been read out
+          mbar_wait(drained_bar, (seg - 1) & 1);
+          tc_fence_after_sync();
         }
-        umma_commit(empty_bar(stage));
+        const int ntile = static_cast<int>(seg_end - j);
+        for (int q = 0; q < ntile; ++q, ++fill) {
+          const int stage = fill % kWStages;
+          mbar_wait(full_bar(stage), (fill / kWStages) & 1);
+          tc_fence_after_sync();
+          const uint32_t dy0 = smem_u32(smem + stage * kWStageBytes);
+          const uint32_t xs0 = dy0 + kDyBytesMax;
+#pragma unroll 1
+          for (int k8 = 0; k8 < 8; ++k8) {       // 16 pixels = tile rows 2*k8, 2*k8+1
+            const uint32_t acc = (q > 0 || k8 > 0) ? 1u : 0u;
+            // B = dY: N chunks 128 B apart, K groups (tile rows) one dY row apart
+            const uint64_t bdesc = umma_smem_desc(dy0 + (2 * k8) * dy_row, /*LBO: next K group*/ dy_row, /*SBO: next N chunk*/ 128);
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              // A = X: plane m -> (halo row 2*k8 + m/6, chunk m%6), pixels kx .. kx+7 of the row
+              const uint32_t a0 = xs0 + (2 * k8) * kXRowPitch + kx * 16;
+              umma_bf16(tmem_base + kx * cout, umma_smem_desc(a0, kXRowPitch, kXPlaneStride), bdesc, idesc_128, acc);
+              umma_bf16(tmem_base + (3 + kx) * cout, umma_smem_desc(a0 + 16 * kXPlaneStride, kXRowPitch, kXPlaneStride),
+                        bdesc, idesc_64, acc);
+            }
+            umma_bf16(tmem_base + 6 * cout, umma_smem_desc(ones_addr, 128, 256), bdesc, idesc_64, acc);
+          }
+          umma_commit(empty_bar(stage));
+        }
+        umma_commit(done_bar);
+        j = seg_end;
       }
-      umma_commit(done_bar);
     }
     __syncwarp();
   } else {
-    // ------------------------------- epilogue: TMEM -> workspace [col][lane 128] -------------------------------
-    mbar_wait_relaxed(done_bar, 0);
-    tc_fence_after_sync();
-    const int ncols = wcols(cout);
-    float* ws = workspace + (static_cast<size_t>(blockIdx.y) * splits + split) * (static_cast<size_t>(kWColsMax) * kWLanes);
+    // ------------------------------- epilogue: TMEM -> workspace slot [col][lane 128] -------------------------------
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const bool any_tiles = split < total_tiles;
     const int l128 = warp * 32 + lane;
-    // columns [0, 3*cout): all 128 lanes ((ky, ci) rows of the M=128 MMAs); columns [3*cout, 7*cout): only TMEM lanes
-    // 0..15 carry data (rows 0..15 of an M=64 accumulator), i.e. warp 0
-    for (int j = 0; j < ncols; j += 16) {
-      if (j >= 3 * cout && warp != 0) break;
-      float v[16];
-      tmem_ld16(taddr + j, v);
-      tmem_ld_wait();
-      if (j < 3 * cout || lane < 16) {
+    int item = item0, seg = 0;
+    for (long long j = j0; j < j1; ++item, ++seg) {
+      const long long seg_end = (sc.prefix[item + 1] < j1) ? sc.prefix[item + 1] : j1;
+      const int cout = items[item].cout;
+      const int ncols = wcols(cout);
+      float* ws = workspace + (static_cast<size_t>(blockIdx.x) * sc.smax + seg) * (static_cast<size_t>(kWColsMax) * kWLanes);
+      mbar_wait_relaxed(done_bar, seg & 1);
+      tc_fence_after_sync();
+      // columns [0, 3*cout): all 128 lanes ((ky, ci) rows of the M=128 MMAs); columns [3*cout, 7*cout): only TMEM lanes
+      // 0..15 carry data (rows 0..15 of an M=64 accumulator), i.e. warp 0
+      for (int c = 0; c < ncols; c += 16) {
+        if (c >= 3 * cout && warp != 0) break;
+        float v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        if (c < 3 * cout || lane < 16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) ws[static_cast<size_t>(j + i) * kWLanes + l128] = any_tiles ? v[i] : 0.f;
+          for (int i = 0; i < 16; ++i) ws[static_cast<size_t>(c + i) * kWLanes + l128] = v[i];
+        }
       }
+      tc_fence_before_sync();
+      mbar_arrive(drained_bar);
+      j = seg_end;
     }
   }
   tc_fence_before_sync();
@@ -177,44 +221,49 @@ wgrad_tc_kernel(const lv_wgrad_item* __restrict__ items, const __grid_constant__
   }
 }
 
-// workspace [item][split][col][lane 128] -> dw / db (+=).  One block per (item, output channel): for each kx the 128
-// lanes of column kx*cout+co are contiguous, permuted through shared memory to OIHW's (ci, ky, kx) order and added to dw
-// as 432 contiguous floats.
+// workspace [cta][slot][col][lane 128] -> dw / db (+=).  One block per (layer, output channel): sums the slots of the
+// CTAs whose job range touched the layer (ascending CTA order: deterministic); for each kx the 128 lanes of column
+// kx*cout+co are contiguous, permuted through shared memory to OIHW's (ci, ky, kx) order and added to dw as 432
+// contiguous floats.
 __global__ void __launch_bounds__(128)
-wgrad_reduce_kernel(const lv_wgrad_item* __restrict__ items, const float* __restrict__ workspace, int splits) {
+wgrad_reduce_kernel(const lv_wgrad_item* __restrict__ items, const __grid_constant__ WSched sc, const float* __restrict__ workspace,
+                    int G) {
+  (void)G;
   __shared__ float sm[9 * kWCin];
-  const lv_wgrad_item it = items[blockIdx.y];
+  const int item = blockIdx.y;
+  const lv_wgrad_item it = items[item];
   const int co = blockIdx.x;
-  if (co >= it.cout) return;
+  const long long jb = sc.prefix[item], je = sc.prefix[item + 1];
+  if (co >= it.cout || je <= jb) return;
   const int cout = it.cout;
   const size_t slot = static_cast<size_t>(kWColsMax) * kWLanes;
-  const float* ws0 = workspace + static_cast<size_t>(blockIdx.y) * splits * slot;
   const int t = threadIdx.x;
-  // rows t = ky*48 + ci of the M=128 accumulators (ky 0, 1 and ky 2 / ci < 32)
-  {
+  const int nslot = sc.ncta[item];
+  const float* wsb = workspace + (static_cast<size_t>(sc.cta_lo[item]) * sc.smax + sc.seg0[item]) * slot;
+  const size_t step = static_cast<size_t>(sc.smax) * slot;
+  const size_t c0 = static_cast<size_t>(0 * cout + co) * kWLanes + t, c1 = static_cast<size_t>(1 * cout + co) * kWLanes + t,
+               c2 = static_cast<size_t>(2 * cout + co) * kWLanes + t;
+  const size_t ce = static_cast<size_t>((3 + (t % 48) / 16) * cout + co) * kWLanes + (t % 16);
+  const size_t cb = static_cast<size_t>(6 * cout + co) * kWLanes;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, e = 0.f, bsum = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < nslot; ++k) {   // ascending CTA order: deterministic
+    // slot of CTA cta_lo + k: the first one at segment seg0, the others at segment 0
+    const float* ws = (k == 0) ? wsb : wsb + k * step - static_cast<size_t>(sc.seg0[item]) * slot;
+    a0 += ws[c0];
+    a1 += ws[c1];
+    a2 += ws[c2];
+    if (t < 48) e += ws[ce];
+    if (t == 64) bsum += ws[cb];
+  }
+  {  // rows t = ky*48 + ci of the M=128 accumulators (ky 0, 1 and ky 2 / ci < 32)
     const int ky = t / kWCin, ci = t % kWCin;
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const float* p = ws0 + static_cast<size_t>(kx * cout + co) * kWLanes + t;
-      float s = 0.f;
-      for (int k = 0; k < splits; ++k) s += p[k * slot];   // fixed order: deterministic
-      sm[ci * 9 + ky * 3 + kx] = s * it.scale;
-    }
+    sm[ci * 9 + ky * 3 + 0] = a0 * it.scale;
+    sm[ci * 9 + ky * 3 + 1] = a1 * it.scale;
+    sm[ci * 9 + ky * 3 + 2] = a2 * it.scale;
   }
-  // rows 0..15 of the M=64 accumulators: ky 2, ci 32..47
-  if (t < 48) {
-    const int kx = t / 16, r = t % 16;
-    const float* p = ws0 + static_cast<size_t>((3 + kx) * cout + co) * kWLanes + r;
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += p[k * slot];
-    sm[(32 + r) * 9 + 6 + kx] = s * it.scale;
-  }
-  if (t == 64 && it.db != nullptr) {
-    const float* p = ws0 + static_cast<size_t>(6 * cout + co) * kWLanes;
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += p[k * slot];
-    it.db[co] += s * it.scale;
-  }
+  if (t < 48) sm[(32 + t % 16) * 9 + 6 + t / 16] = e * it.scale;   // rows 0..15 of the M=64 accumulators: ky 2, ci 32..47
+  if (t == 64 && it.db != nullptr) it.db[co] += bsum * it.scale;
   __syncthreads();
   float* dst = it.dw + (static_cast<size_t>(co) * it.cin_total + it.cin_off) * 9;
   for (int j = t; j < 9 * kWCin; j += 128) dst[j] += sm[j];
@@ -320,9 +369,58 @@ static bool tc_eligible(const lv_wgrad_item* items, int count) {
   return true;
 }
 
+static long long item_tiles(const lv_wgrad_item& a) {
+  return static_cast<long long>(a.n) * ((a.h + kWT_H - 1) / kWT_H) * ((a.w + kWT_W - 1) / kWT_W);
+}
+
+// job schedule of items[0..count) (count <= kWMaxItems) on at most `max_ctas` CTAs; returns the grid size (0: no work)
+static int make_sched(const lv_wgrad_item* items, int count, long long max_ctas, WSched* sc) {
+  sc->count = count;
+  long long j = 0;
+  for (int k = 0; k < count; ++k) {
+    sc->prefix[k] = static_cast<int>(j);
+    j += item_tiles(items[k]);
+  }
+  for (int k = count; k <= kWMaxItems; ++k) sc->prefix[k] = static_cast<int>(j);
+  sc->jobs = j;
+  if (j == 0) { sc->smax = 1; return 0; }
+  long long G = max_ctas < sm_count() ? max_ctas : sm_count();
+  if (G > 512) G = 512;   // wgrad_reduce_kernel's slot list
+  if (G > j) G = j;
+  if (G < 1) G = 1;
+  int smax = 1;
+  for (int b = 0; b < G; ++b) {
+    const long long s0 = wstart(j, b, static_cast<int>(G)), s1 = wstart(j, b + 1, static_cast<int>(G));
+    const int n = witem(*sc, s1 - 1) - witem(*sc, s0) + 1;
+    if (n > smax) smax = n;
+  }
+  sc->smax = smax;
+  for (int k = 0; k < count; ++k) {
+    const long long jb = sc->prefix[k], je = sc->prefix[k + 1];
+    sc->cta_lo[k] = sc->ncta[k] = sc->seg0[k] = 0;
+    if (je <= jb) continue;
+    // CTA owning job x: the largest b with jobs*b/G <= x
+    auto owner = [&](long long x) { return static_cast<int>(((x + 1) * G + j - 1) / j - 1); };
+    const int lo = owner(jb), hi = owner(je - 1);
+    sc->cta_lo[k] = static_cast<short>(lo);
+    sc->ncta[k] = static_cast<short>(hi - lo + 1);
+    sc->seg0[k] = static_cast<short>(k - witem(*sc, wstart(j, lo, static_cast<int>(G))));
+  }
+  return static_cast<int>(G);
+}
+
 long long wgrad_workspace_bytes(const lv_wgrad_item* items, int count, int splits) {
   if (count <= 0 || splits <= 0 || !tc_eligible(items, count)) return 0;
-  return static_cast<long long>(count) * splits * kWColsMax * kWLanes * sizeof(float);
+  long long total = 0;
+  WSched sc;
+  for (int first = 0; first < count; first += kWMaxItems) {
+    const int cnt = (count - first < kWMaxItems) ? count - first : kWMaxItems;
+    for (int k = 0; k < cnt; ++k)
+      if (item_tiles(items[first + k]) >= (1ll << 31) / kWMaxItems) return -1;
+    const int G = make_sched(items + first, cnt, static_cast<long long>(splits) * cnt, &sc);
+    total += static_cast<long long>(G) * sc.smax * kWColsMax * kWLanes * sizeof(float);
+  }
+  return total > 16 ? total : 16;
 }
 
 int wgrad_simt(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int count, int splits, cudaStream_t stream) {
@@ -420,22 +518,28 @@ int wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int c
     LV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
     configured = true;
   }
-  static WMaps maps;   // staging only; the launch copies it by value
+  static WMaps maps;   // staging only; the launches copy them by value
+  static WSched sc;
   const size_t slot = static_cast<size_t>(kWColsMax) * kWLanes;
+  float* ws = static_cast<float*>(workspace);
   for (int first = 0; first < count; first += kWMaxItems) {
     const int cnt = (count - first < kWMaxItems) ? count - first : kWMaxItems;
     for (int k = 0; k < cnt; ++k) {
       const lv_wgrad_item& a = items_host[first + k];
+      LV_CHECK_ARG(item_tiles(a) < (1ll << 31) / kWMaxItems, "wgrad: item %d has too many tiles", first + k);
+      if (item_tiles(a) == 0) continue;
       rc = tile_map(a.dy, a.n, a.h, a.w, a.cout / 8, kWT_W, kWT_H, &maps.dy[k]);
       if (rc != LV_OK) return rc;
       rc = tile_map(a.x, a.n, a.h, a.w, kWCh, kWHaloW, kWHaloH, &maps.x[k]);
       if (rc != LV_OK) return rc;
     }
-    float* ws = static_cast<float*>(workspace) + static_cast<size_t>(first) * splits * slot;
-    wgrad_tc_kernel<<<dim3(splits, cnt), kWThreads, kWSmem, stream>>>(items_dev + first, maps, ws, splits);
+    const int G = make_sched(items_host + first, cnt, static_cast<long long>(splits) * cnt, &sc);
+    if (G == 0) continue;
+    wgrad_tc_kernel<<<G, kWThreads, kWSmem, stream>>>(items_dev + first, maps, sc, ws);
     LV_LAUNCH_OK();
-    wgrad_reduce_kernel<<<dim3(64, cnt), 128, 0, stream>>>(items_dev + first, ws, splits);
+    wgrad_reduce_kernel<<<dim3(64, cnt), 128, 0, stream>>>(items_dev + first, sc, ws, G);
     LV_LAUNCH_OK();
+    ws += static_cast<size_t>(G) * sc.smax * slot;
   }
   return LV_OK;
 }

@@ -361,9 +361,8 @@ class LarvaEngine:
             groups = [sum(per_body[g:g + k], []) for g in range(0, len(per_body), k)]
             cost = 0.0
             for grp in groups:
-                sp = splits if splits > 0 else max(1, min(tiles, self.sm_count // len(grp)))
-                waves = -(-len(grp) * sp // self.sm_count)
-                cost += waves * (-(-tiles // sp) * 1.7 + 25.0)
+                ctas = min(self.sm_count, len(grp) * tiles, len(grp) * splits if splits > 0 else self.sm_count)
+                cost += -(-len(grp) * tiles // ctas) * 1.4 + 25.0
             if best is None or cost < best[0] - 1e-9:
                 best = (cost, groups)
         b.wgrad = [self._make_wgrad(grp, tiles, splits) for grp in best[1]]
@@ -371,8 +370,9 @@ class LarvaEngine:
 
     def _make_wgrad(self, items, tiles, splits):
         if splits <= 0:
-            # the wgrad CTA owns the whole TMEM (1 CTA/SM): one wave of SMs, at most one split per tile
-            splits = max(1, min(tiles, self.sm_count // len(items)))
+            # the library cuts the launch's tile jobs into min(splits * layers, SMs) equal ranges (1 CTA/SM): ask for
+            # at least one range per SM
+            splits = max(1, min(tiles, -(-self.sm_count // len(items))))
         return ops.WgradBatch(items, splits, self.device)
 
     def set_data_parallel(self, world_size, process_group=None):
