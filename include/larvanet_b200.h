@@ -97,10 +97,11 @@ typedef struct lv_wgrad_item {
   int32_t dtype;
   const void* x;             /* NHWC [n,h,w,cin]  layer input saved by the forward pass                    */
   const void* dy;            /* NHWC [n,h,w,cout] gradient wrt the conv output (before bias)               */
-  float* dw;                 /* fp32 OIHW, ACCUMULATED INTO (dw += scale * sum)                            */
-  float* db;                 /* fp32 [cout], accumulated into; NULL to skip                                */
+  float* dw;                 /* fp32 OIHW, ACCUMULATED INTO (dw += scale * sum) unless `overwrite`         */
+  float* db;                 /* fp32 [cout], same; NULL to skip                                            */
   float scale;
-  int32_t reserved;
+  int32_t overwrite;         /* bf16 tensor-core path only: 1 = store instead of accumulate (this item is the */
+                             /* only writer of its dw slice / db, so the caller need not zero them first)  */
 } lv_wgrad_item;
 
 /* Weight re-pack work item: fp32 OIHW master weight [O, I, 3, 3] -> packed operand for lv_conv3x3.

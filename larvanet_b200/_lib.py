@@ -45,7 +45,7 @@ class WgradItem(C.Structure):
         ('cin', C.c_int32), ('cout', C.c_int32), ('cin_total', C.c_int32), ('cin_off', C.c_int32),
         ('dtype', C.c_int32),
         ('x', C.c_void_p), ('dy', C.c_void_p), ('dw', C.c_void_p), ('db', C.c_void_p),
-        ('scale', C.c_float), ('reserved', C.c_int32),
+        ('scale', C.c_float), ('overwrite', C.c_int32),
     ]
 
 

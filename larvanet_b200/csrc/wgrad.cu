@@ -263,10 +263,14 @@ wgrad_reduce_kernel(const lv_wgrad_item* __restrict__ items, const __grid_consta
     sm[ci * 9 + ky * 3 + 2] = a2 * it.scale;
   }
   if (t < 48) sm[(32 + t % 16) * 9 + 6 + t / 16] = e * it.scale;   // rows 0..15 of the M=64 accumulators: ky 2, ci 32..47
-  if (t == 64 && it.db != nullptr) it.db[co] += bsum * it.scale;
+  if (t == 64 && it.db != nullptr) it.db[co] = bsum * it.scale + (it.overwrite ? 0.f : it.db[co]);
   __syncthreads();
   float* dst = it.dw + (static_cast<size_t>(co) * it.cin_total + it.cin_off) * 9;
-  for (int j = t; j < 9 * kWCin; j += 128) dst[j] += sm[j];
+  if (it.overwrite) {
+    for (int j = t; j < 9 * kWCin; j += 128) dst[j] = sm[j];
+  } else {
+    for (int j = t; j < 9 * kWCin; j += 128) dst[j] += sm[j];
+  }
 }
 
 // ============================================================================================

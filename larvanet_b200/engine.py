@@ -118,6 +118,7 @@ class LarvaEngine:
         self.wgrad_splits = int(os.environ.get('LARVANET_B200_WGRAD_SPLITS', '0'))
         self.arena = ParamArena(module, self.device)
         self._conv_layers = self._enumerate_convs()
+        self._head_grad_slice = self.arena.slice_of('head.')
         self._alloc_packed()
         self._packed_version = None
         self._packed_bwd = False
@@ -365,6 +366,9 @@ class LarvaEngine:
                 cost += -(-len(grp) * tiles // ctas) * 1.4 + 25.0
             if best is None or cost < best[0] - 1e-9:
                 best = (cost, groups)
+        for grp in best[1]:
+            for it in grp:
+                it['overwrite'] = True     # every conv weight / bias slice has exactly one writer per step
         b.wgrad = [self._make_wgrad(grp, tiles, splits) for grp in best[1]]
         return b
 
@@ -385,7 +389,13 @@ class LarvaEngine:
         hw, hb = self._w('head.feature_extraction')
         scale = b.scale / self.world_size
         b.loss_sum.zero_()
-        self.arena.grad.zero_()
+        if self.simt or self.act_dtype != torch.bfloat16:
+            self.arena.grad.zero_()           # the CUDA-core weight-gradient kernels accumulate with atomics
+        else:
+            # the tensor-core weight-gradient reduction STORES every conv gradient (items carry overwrite=1); only the
+            # head conv's gradient is accumulated with atomics and needs a zeroed slice
+            lo, hi = self._head_grad_slice
+            self.arena.grad[lo:hi].zero_()
         ops.head_bicubic(b.x, hw, hb, b.f0, b.base)
         self._begin_chain()
         # ---------------- forward ----------------

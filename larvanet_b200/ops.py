@@ -241,6 +241,7 @@ class WgradBatch:
             hi.x, hi.dy = _ptr(x, None, 'x'), _ptr(dy, x.dtype, 'dy')
             hi.dw, hi.db = _ptr(dw, torch.float32, 'dw'), _ptr(db, torch.float32, 'db')
             hi.scale = float(it.get('scale', 1.0))
+            hi.overwrite = int(bool(it.get('overwrite', False)))
             self._keep.append((x, dy, dw, db))
         raw = bytes(self.host)
         self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
