@@ -178,15 +178,22 @@ class LarvaEngine:
 
     def repack(self, backward=False, force=False):
         """Refresh the packed bf16/fp32 conv operands from the fp32 master weights when they changed."""
-        ver = self.arena.version()
-        if not force and ver == self._packed_version and (self._packed_bwd or not backward):
-            return
-        ops.pack_weights_prebuilt(self._pack_arr_all if backward else self._pack_arr_fwd)
-        self._packed_version = ver
+        if not force and self._packed_version is not None:
+            if self.arena.version() == self._packed_version and (self._packed_bwd or not backward):
+                return
+        ops.pack_weights_prebuilt(self._pack_arr_all if backward else self._pack_arr_fwd)   # launch first, book-keep after
+        self._packed_version = self.arena.version()
         self._packed_bwd = backward
 
     def mark_weights_changed(self):
         self._packed_version = None
+
+    def weights_updated(self):
+        """Called by FusedAdamW right after its update kernel: re-pack NOW, on the same stream, in the form the last
+        pass used -- the next step's first launch is then not preceded by host-side re-pack work while the GPU idles."""
+        self._packed_version = None
+        if self._packed_bwd:
+            self.repack(backward=True)
 
     # ------------------------------------------------------------------ helpers
     def _w(self, prefix):
@@ -471,7 +478,6 @@ class LarvaEngine:
         b = ent[0]
         b.x.copy_(x, non_blocking=True)
         b.truth.copy_(truth, non_blocking=True)
-        self.arena.attach_grads()
         if self.use_graphs and not self.simt:
             if ent[1] is None:
                 g, nl = _capture_graph(lambda: self._run_train(b))
@@ -484,6 +490,7 @@ class LarvaEngine:
                 self._run_train(b)
         else:
             self._run_train(b)
+        self.arena.attach_grads()   # host-only book-keeping, after the launches so that the GPU is already busy
         if self.world_size > 1:
             from . import dist as lvdist
             for work in lvdist.allreduce_gradients(self.arena.grad, b.loss_sum, self.process_group):

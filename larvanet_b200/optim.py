@@ -50,4 +50,7 @@ class FusedAdamW(torch.optim.AdamW):
         a = self._engine.arena
         ops.adamw_step(a.flat, a.grad, self._exp_avg, self._exp_avg_sq, g['lr'], g['betas'][0], g['betas'][1], g['eps'],
                        g['weight_decay'], self._steps, 1.0)
-        self._engine.mark_weights_changed()
+        if hasattr(self._engine, 'weights_updated'):
+            self._engine.weights_updated()
+        else:
+            self._engine.mark_weights_changed()
