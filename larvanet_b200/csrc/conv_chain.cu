@@ -75,12 +75,22 @@ __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ void red_relaxed_gpu_add(uint32_t* p, uint32_t v) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// ld.acquire.gpu compiles to LD + CCTL.IVALL (invalidate the SM's whole L1) and that is where a polling warp's samples pile
+// up in the ncu source view: poll with relaxed loads, then ONE acquire load of the satisfied flag (every writer is a
+// release RMW, so whatever value it reads continues the release sequence).
 __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t need) {
+  if (ld_acquire_gpu(p) >= need) return;      // common case: already there
   uint32_t spins = 0;
-  while (ld_acquire_gpu(p) < need) {
-    __nanosleep(64);
+  while (ld_relaxed_gpu(p) < need) {
+    __nanosleep(32);
     if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
   }
+  (void)ld_acquire_gpu(p);
 }
 __device__ __forceinline__ uint4 ldcg16(const __nv_bfloat16* p) {
   return __ldcg(reinterpret_cast<const uint4*>(p));   // L2 only: other CTAs rewrite these buffers during the kernel
