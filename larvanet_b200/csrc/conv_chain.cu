@@ -658,7 +658,7 @@ int conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, long lon
                sync_ws_bytes, (tt + 1) * 4);
   g.total_tiles = static_cast<int>(tt);
 
-  static chain::Params params;   // staging only; the launch copies it by value
+  static thread_local chain::Params params;   // staging only; the launch copies it by value
   for (int i = 0; i < count; ++i) params.layer[i] = layers[i];
   auto kern = chain::conv3x3_chain_kernel<48, 48, 4>;
   static bool configured = false;

@@ -522,8 +522,8 @@ int wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int c
     LV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
     configured = true;
   }
-  static WMaps maps;   // staging only; the launches copy them by value
-  static WSched sc;
+  static thread_local WMaps maps;   // staging only; the launches copy them by value
+  static thread_local WSched sc;
   const size_t slot = static_cast<size_t>(kWColsMax) * kWLanes;
   float* ws = static_cast<float*>(workspace);
   for (int first = 0; first < count; first += kWMaxItems) {
