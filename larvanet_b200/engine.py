@@ -77,6 +77,25 @@ class _Bufs:
     pass
 
 
+class DeviceScalar:
+    """The step's loss: a float64 device accumulator times a host-side factor, read back lazily.  `.item()` / `float()`
+    are the only device->host traffic (8 bytes) and no extra kernels are launched for the scaling."""
+
+    def __init__(self, acc, scale):
+        self._acc, self._scale = acc, float(scale)
+
+    def item(self):
+        return float(self._acc.item()) * self._scale
+
+    __float__ = item
+
+    def tensor(self):
+        return self._acc[0] * self._scale
+
+    def __repr__(self):
+        return f'DeviceScalar({self.item():.6f})'
+
+
 def _capture_graph(run):
     """Warm up `run()` eagerly, then capture it into a CUDA graph.  Returns (graph, launches) or (None, 0) when the
     capture was invalidated (seen once after unrelated allocator churn); the caller then keeps launching the same CUDA
@@ -458,7 +477,7 @@ class LarvaEngine:
 
     def train_step(self, x, truth, keep_exits=False):
         """One forward+backward.  Leaves d(loss)/d(param) in the gradient arena (== every param.grad) and returns the
-        multi-exit loss as a 0-dim float64 CUDA tensor (no host sync).  Restates models/LarvaNet.py:102-113 /
+        multi-exit loss as a lazily read `DeviceScalar` (`.item()` / `float()`; no host sync, no extra launch before that).  Restates models/LarvaNet.py:102-113 /
         models/LarvaNetV2.py:105-120 (everything before optim.step())."""
         n, _, h, w = (int(v) for v in x.shape)
         if tuple(truth.shape) != (n, 3, 4 * h, 4 * w):
@@ -499,7 +518,7 @@ class LarvaEngine:
         numel = n * 3 * 16 * h * w * self.world_size
         self.last_exits = b.exits
         self._last_train = b
-        return b.loss_sum[0] / (float(numel) * denom)
+        return DeviceScalar(b.loss_sum, 1.0 / (float(numel) * denom))
 
     def saved_activations(self):
         """The forward activations the last train_step saved for its backward pass, as NCHW float32 CPU tensors keyed
