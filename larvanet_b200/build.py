@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(CSRC, 'build')
 LIB = os.path.join(HERE, 'liblarvanet_b200.so')
-SOURCES = ['capi.cu', 'conv_tc.cu', 'conv_tc_ky.cu', 'conv_chain.cu', 'conv_simt.cu', 'wgrad.cu', 'head.cu', 'layout.cu']
+SOURCES = ['capi.cu', 'conv_tc.cu', 'conv_tc_ky.cu', 'conv_chain.cu', 'conv_strip.cu', 'conv_simt.cu', 'wgrad.cu', 'head.cu', 'layout.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
 

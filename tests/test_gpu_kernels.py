@@ -404,3 +404,17 @@ def test_uint8_and_psnr_helpers():
     assert sq.item() == ref_sq
     psnr = 10.0 * np.log10(255.0 ** 2 / (sq.item() / img.size))
     assert abs(psnr - O.image_psnr(o8, t8)) < 1e-4
+
+
+def test_cluster_resident_strip_chain_is_bit_exact():
+    """The opt-in cluster-resident chain (conv_strip.cu, LARVANET_B200_STRIP=1: activations in shared memory, halo columns
+    through DSMEM) must give the per-layer launches' results bit for bit.  Runs in a subprocess: the switch is read once."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LARVANET_B200_STRIP='1')
+    for shape in (('2', '37', '45'), ('3', '48', '48')):
+        out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'strip_debug2.py'), *shape], env=env, cwd=root,
+                             capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr[-400:]
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith('prefix')]
+        assert len(lines) >= 10 and all(ln.rstrip().endswith('[]') for ln in lines), out.stdout[-600:]

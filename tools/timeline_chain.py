@@ -33,7 +33,7 @@ def main():
     lib.lv_debug_set_timeline(None)
     t = tl.cpu().view(9, 64, 4)
     t0 = int(t[t > 0].min())
-    names = {0: ('prod', ['deps_ok', 'got_empty', 'issued', 'polled']),
+    names = {0: ('prod', ['deps_ok/lyr_wait', 'got_empty/lyr_ok', 'issued/w_ok', 'polled/fenced']),
              3: ('pub ', ['arrived', 'released', '-', '-']),
              4: ('st h0', ['q0', 'q1', 'q2', 'q3']), 5: ('st h1', ['q0', 'q1', 'q2', 'q3']),
              6: ('rl h0', ['q0', 'q1', 'q2', 'q3']), 7: ('rl h1', ['q0', 'q1', 'q2', 'q3']),
