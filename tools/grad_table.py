@@ -26,7 +26,8 @@ def main():
               f'cos={np.sum(g*r)/np.linalg.norm(g)/np.linalg.norm(r):.5f}')
     # head: compare against oracle head wgrad using the DEVICE dfin (isolates the head wgrad kernel)
     b = eng._train[(2, 12, 10, True)][0]
-    dfin = b.dfin[0].float().cpu().numpy().transpose(0, 3, 1, 2).astype(np.float64)
+    # planar-8 [n, h, c/8, w, 8] -> NCHW
+    dfin = b.dfin[0].float().cpu().permute(0, 2, 4, 1, 3).reshape(2, 48, 12, 10).numpy().astype(np.float64)
     _, dwh, dbh = O.conv2d_backward(lr.astype(np.float64), np.zeros((48, 3, 3, 3)), dfin)
     scale = b.scale
     gh = m.get_model().head.feature_extraction.weight.grad.cpu().numpy()
