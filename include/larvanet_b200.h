@@ -129,7 +129,8 @@ int lv_device_check(int dev, int* sm_count);
 
 /* bytes of the packed weight for a conv with `cout` outputs and `cin_total` inputs */
 int64_t lv_packed_weight_bytes(int cout, int cin_total, int dtype);
-/* batched pack: `items` is a HOST array (copied by value into the launch); count <= 64 per call */
+/* batched pack: `items` is a HOST array (copied by value into the launch); count <= LV_PACK_MAX_ITEMS per call */
+#define LV_PACK_MAX_ITEMS 128
 int lv_pack_conv3x3_weights(const lv_pack_item* items, int count, void* stream);
 
 /* the conv (see lv_conv_args).  `max_ctas` <= 0 lets the library choose (persistent grid).

@@ -12,7 +12,7 @@ namespace lv {
 
 int pick_ntile(int cout_pad);
 
-constexpr int kMaxPackItems = 64;
+constexpr int kMaxPackItems = 128;   // LV_PACK_MAX_ITEMS: 128 x 80 B kernel parameter
 struct PackItemDev {
   const float* w;
   void* packed;

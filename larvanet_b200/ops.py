@@ -69,12 +69,12 @@ def packed_weight_bytes(cout, cin_total, dt):
 
 
 def build_pack_arrays(items):
-    """Marshal pack items once: list of (ctypes PackItem array, count) chunks of <= 64 (the C-ABI's per-call limit).
+    """Marshal pack items once: list of (ctypes PackItem array, count) chunks of <= 128 (the C-ABI's per-call limit).
     items: list of dicts(w=fp32 OIHW tensor, packed=uint8/any tensor, transpose, i_off, i_cnt, cin, dtype, wlayout).
     The tensors must stay alive (and keep their storage) for as long as the arrays are used."""
     out = []
-    for start in range(0, len(items), 64):
-        chunk = items[start:start + 64]
+    for start in range(0, len(items), 128):
+        chunk = items[start:start + 128]
         arr = (PackItem * len(chunk))()
         for k, it in enumerate(chunk):
             w = it['w']
