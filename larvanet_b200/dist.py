@@ -52,6 +52,48 @@ def allreduce_gradients(flat_grad, loss_sum=None, group=None):
     return works
 
 
+class SymmetricGradExchange:
+    """In-place SUM all-reduce of the gradient arena through symmetric (peer-mapped) memory over NVLink: the two-shot
+    kernel of torch.distributed._symmetric_memory (every rank reduces 1/G of the buffer straight out of its peers' HBM,
+    then every rank gathers), stream-ordered, ~3x lower latency than NCCL's ring / tree for this 3.3 MB latency-bound
+    message.  The arena has to live in a symmetric allocation: `buffer` replaces the engine's gradient arena.
+
+    Construction is collective.  Every rank reports success or failure and the group only switches over if ALL ranks
+    succeeded; otherwise everybody keeps the NCCL all-reduce (`allreduce_gradients`)."""
+
+    def __init__(self, numel, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.group_name = self.group.group_name
+        world = dist.get_world_size(self.group)
+        pad = 4 * 32 * world                       # 16-byte vectors x 32 lanes x ranks: keeps every rank's share aligned
+        self.numel = (int(numel) + pad - 1) // pad * pad
+        self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+        self.buffer.zero_()
+        self.handle = symm_mem.rendezvous(self.buffer, self.group_name)
+
+    def allreduce_(self):
+        torch.ops.symm_mem.two_shot_all_reduce_(self.buffer, 'sum', self.group_name)
+
+    @staticmethod
+    def try_create(numel, device, group=None):
+        """Collective: returns an exchange on every rank or None on every rank."""
+        ok, ex = 1, None
+        if os.environ.get('LARVANET_B200_SYMM_ALLREDUCE', '1') == '0':
+            ok = 0
+        else:
+            try:
+                ex = SymmetricGradExchange(numel, device, group)
+                ex.allreduce_()                   # one warm-up exchange (zeros) also proves the kernel runs here
+                torch.cuda.synchronize(device)
+            except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", agreed on collectively below
+                ok, ex = 0, None
+                print(f'[larvanet_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL')
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return ex if int(flag.item()) == 1 else None
+
+
 def frames_for_rank(num_frames, rank, world):
     """Round-robin frame indices for batch-sharded inference (no collective)."""
     return list(range(rank, num_frames, world))

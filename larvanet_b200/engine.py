@@ -54,6 +54,14 @@ class ParamArena:
             off += k
         self.total = total
 
+    def replace_grad(self, flat):
+        """Move the gradient arena into `flat` (>= total elements, e.g. a symmetric-memory allocation)."""
+        self.grad = flat
+        for n, (off, k) in self.offsets.items():
+            self.grad_views[n] = flat[off:off + k].view(self.params[n].shape)
+            if self.params[n].grad is not None:
+                self.params[n].grad = None
+
     def attach_grads(self):
         for n, p in self.params.items():
             if p.requires_grad and p.grad is not self.grad_views[n]:
@@ -153,6 +161,7 @@ class LarvaEngine:
         # data parallel
         self.world_size = 1
         self.process_group = None
+        self._symm = None       # symmetric-memory gradient exchange (data parallel), else NCCL
 
     # ------------------------------------------------------------------ layers / packed weights
     def _enumerate_convs(self):
@@ -406,9 +415,16 @@ class LarvaEngine:
         return ops.WgradBatch(items, splits, self.device)
 
     def set_data_parallel(self, world_size, process_group=None):
+        """Collective when world_size > 1 (every rank must call it)."""
         self.world_size = int(world_size)
         self.process_group = process_group
         self._train.clear()
+        self._symm = None
+        if self.world_size > 1 and self.device.type == 'cuda':
+            from . import dist as lvdist
+            self._symm = lvdist.SymmetricGradExchange.try_create(self.arena.total, self.device, process_group)
+            if self._symm is not None:
+                self.arena.replace_grad(self._symm.buffer)
 
     def _run_train(self, b):
         """forward with saved activations + fused losses, then backward-data chain and batched weight gradients."""
@@ -512,7 +528,13 @@ class LarvaEngine:
         self.arena.attach_grads()   # host-only book-keeping, after the launches so that the GPU is already busy
         if self.world_size > 1:
             from . import dist as lvdist
-            for work in lvdist.allreduce_gradients(self.arena.grad, b.loss_sum, self.process_group):
+            if self._symm is not None:
+                # 8-byte loss on NCCL's stream, the gradients through peer memory on this one, concurrently
+                works = lvdist.allreduce_gradients(b.loss_sum, None, self.process_group)
+                self._symm.allreduce_()
+            else:
+                works = lvdist.allreduce_gradients(self.arena.grad, b.loss_sum, self.process_group)
+            for work in works:
                 work.wait()   # stream-ordered on NCCL: enqueues a wait on the current stream, no host sync
         denom = self.m + 1 if self.v2 else self.m
         numel = n * 3 * 16 * h * w * self.world_size

@@ -23,7 +23,7 @@ def main():
         eng = m._engine(); eng.set_data_parallel(world)
         b, e = lvdist.shard_range(8, rank, world)
         loss = eng.train_step(torch.from_numpy(lr[b:e]).cuda(), torch.from_numpy(hr[b:e]).cuda()).item()
-        g_dp = eng.arena.grad.clone()
+        g_dp = eng.arena.grad[:eng.arena.total].clone()
         # single-rank reference on the whole batch (same process, world_size 1)
         m1 = make(blocks, v2); m1.get_model().load_state_dict(sd)
         e1 = m1._engine()
