@@ -153,3 +153,40 @@ def test_edsr_plugin_surface():
     assert not m.get_model().mean_shift.weight.requires_grad       # frozen like the reference (models/edsr.py:135-136)
     with pytest.raises(NotImplementedError):
         m.train_step([], 4, [])
+
+
+def test_workspace_size_queries_need_no_gpu():
+    """Pure host arithmetic of the C-ABI: chain flag workspace and the stream-K style weight-gradient schedule."""
+    lib = _lib.load()
+    assert lib.lv_conv_chain_workspace_bytes(16, 48, 48) == (16 * 3 * 6 + 1) * 4
+    assert lib.lv_conv_chain_workspace_bytes(1, 180, 320) == (12 * 40 + 1) * 4
+    assert lib.lv_conv_chain_workspace_bytes(0, 48, 48) == 4
+    slot = 448 * 128 * 4                      # accumulator columns x TMEM lanes x fp32
+
+    def items(shapes):
+        arr = (_lib.WgradItem * len(shapes))()
+        for it, (n, h, w) in zip(arr, shapes):
+            it.n, it.h, it.w, it.cin, it.cout, it.cin_total, it.cin_off, it.dtype = n, h, w, 48, 48, 48, 0, _lib.LV_BF16
+            it.x, it.dy, it.dw = 0x1000, 0x2000, 0x3000
+        return arr
+    # 40 layers x 288 tiles on <= 148 CTAs: every CTA's range touches at most two layers -> two slots per CTA
+    b = lib.lv_wgrad_workspace_bytes(items([(16, 48, 48)] * 40), 40, 4)
+    assert b == 148 * 2 * slot
+    # fewer jobs than SMs: one CTA per tile, one slot each
+    assert lib.lv_wgrad_workspace_bytes(items([(1, 16, 8)] * 3), 3, 50) == 3 * slot
+    # the requested splits bound the grid; layers without tiles get no slots
+    assert lib.lv_wgrad_workspace_bytes(items([(2, 32, 16), (0, 32, 16)]), 2, 2) == 4 * slot
+    # fp32 items take the CUDA-core path: no workspace
+    f32 = items([(1, 16, 8)])
+    f32[0].dtype = _lib.LV_F32
+    assert lib.lv_wgrad_workspace_bytes(f32, 1, 4) == 0
+
+
+def test_device_scalar_reads_lazily():
+    import torch
+    from larvanet_b200.engine import DeviceScalar
+    acc = torch.tensor([12.0], dtype=torch.float64)
+    s = DeviceScalar(acc, 0.25)
+    assert s.item() == 3.0 and float(s) == 3.0
+    acc[0] = 20.0                                  # read at call time, not at construction
+    assert s.item() == 5.0 and float(s.tensor()) == 5.0
