@@ -6,11 +6,14 @@
 // weights), pipeline fill and drain (measured 6-8 us per layer for ~2 us of tensor work).  Here the CTAs stay resident
 // for all layers and the layers are chained by data flow instead of kernel boundaries:
 //
-//   * every layer has the same tile grid (16x8 output pixels, conv_tc.cu's implicit GEMM); done[tile] counts the
-//     epilogue warps that have finished that tile (4 per layer, red.release.gpu by each warp);
-//   * the job (layer l, tile X) may start when all 9 tiles around X have finished every earlier layer
-//     (done >= 4*l, ld.acquire.gpu polls by every halo producer warp).  That one rule covers the halo reads, the same-tile
-//     residual / mask reads of the epilogue, and the write-after-read hazards of ping-pong activation buffers;
+//   * every layer has the same tile grid (16x8 output pixels, conv_tc.cu's implicit GEMM); done[tile] counts finished
+//     (layer, tile) jobs, 4 per job.  The epilogue warps arrive on a CTA-scope mbarrier after their stores and move on; a
+//     dedicated publisher warp turns "all 4 warps arrived" into one red.release.gpu, which is what waits for the SM's
+//     store acknowledgements (1.1-1.5k clk);
+//   * the job (layer l, tile X) may start when all 9 tiles around X have finished every earlier layer (done >= 4*l;
+//     every halo producer warp polls with relaxed loads and finishes with one ld.acquire.gpu).  That one rule covers the
+//     halo reads, the same-tile residual / mask reads of the epilogue, and the write-after-read hazards of ping-pong
+//     activation buffers;
 //   * the halo / MMA / epilogue pipeline never drains between layers: the producers run ahead into layer l+1 while
 //     the epilogue of layer l is still in flight, and the weights of layer l+1 are prefetched by TMA into the next of
 //     three shared-memory weight buffers at the start of layer l;
