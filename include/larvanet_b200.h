@@ -213,6 +213,21 @@ int lv_l1_loss_grad(const float* out_hr, const float* truth_hr, double* loss_sum
  * Fused multi-tensor AdamW over a flat fp32 parameter/gradient arena (torch.optim.AdamW defaults,
  * models/LarvaNet.py:86-88,114).  `grad_scale` multiplies the gradient first (DP mean / loss scaling).
  */
+/* One packed conv weight for lv_adamw_pack_step: OIHW fp32 [48, cin_total, 3, 3] at element offset `w_off` of the parameter
+ * arena, its LV_BF16 / LV_W_TAP_MAJOR forward operand and the backward-data operand of every 48-channel source slice. */
+typedef struct lv_fused_conv {
+  int64_t w_off;
+  int32_t cout, cin_total;
+  void* fwd;
+  void* bwd[LV_MAX_SRC];
+} lv_fused_conv;
+
+/* lv_adamw_step + lv_pack_conv3x3_weights (forward and backward-data operands) of the listed convs in ONE kernel; `convs`
+ * is a HOST array (<= 64, sorted by w_off, disjoint); parameters outside the listed weights get the plain update. */
+int lv_adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                       const lv_fused_conv* convs, int nconv, void* stream);
+
 int lv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                   void* stream);

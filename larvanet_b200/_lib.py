@@ -49,6 +49,11 @@ class WgradItem(C.Structure):
     ]
 
 
+class FusedConv(C.Structure):
+    _fields_ = [('w_off', C.c_int64), ('cout', C.c_int32), ('cin_total', C.c_int32), ('fwd', C.c_void_p),
+                ('bwd', C.c_void_p * LV_MAX_SRC)]
+
+
 class PackItem(C.Structure):
     _fields_ = [
         ('w', C.c_void_p), ('packed', C.c_void_p),
@@ -80,6 +85,8 @@ SIGNATURES = {
     'lv_image_to_uint8': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'lv_psnr_sqsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
     'lv_l1_loss_grad': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_void_p]),
+    'lv_adamw_pack_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float,
+                                                                                      C.POINTER(FusedConv), C.c_int, C.c_void_p]),
     'lv_adamw_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_void_p]),
     'lv_launch_count': (C.c_int64, []),
 }

@@ -53,6 +53,8 @@ int nhwc_to_nchw(const void*, float*, int, int, int, int, int, cudaStream_t);
 int l1_loss_grad(const float*, const float*, double*, void*, int, int, int, int, int, cudaStream_t);
 int adamw_step(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float, cudaStream_t);
 int image_to_uint8(const float*, uint8_t*, long long, cudaStream_t);
+int adamw_pack_step(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float,
+                    const lv_fused_conv*, int, cudaStream_t);
 int psnr_sqsum(const float*, const float*, double*, int, int, int, int, int, cudaStream_t);
 long long wgrad_workspace_bytes(const lv_wgrad_item*, int, int);
 int wgrad(const lv_wgrad_item*, const lv_wgrad_item*, int, int, void*, cudaStream_t);
@@ -211,6 +213,14 @@ int lv_l1_loss_grad(const float* out_hr, const float* truth_hr, double* loss_sum
                     int w_, int dtype, void* stream) {
   LV_CHECK_ARG(out_hr && truth_hr, "l1: null pointer");
   return l1_loss_grad(out_hr, truth_hr, loss_sum, grad_sign, n, c, h, w_, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int lv_adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                       const lv_fused_conv* convs, int nconv, void* stream) {
+  LV_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adamw+pack: null pointer");
+  return adamw_pack_step(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                         convs, nconv, static_cast<cudaStream_t>(stream));
 }
 
 int lv_image_to_uint8(const float* src, uint8_t* dst, int64_t numel, void* stream) {

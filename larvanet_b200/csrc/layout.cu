@@ -300,4 +300,144 @@ int adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_s
   return LV_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// AdamW + bf16 operand re-pack in ONE kernel.  A block owns "bricks" of a conv weight: 8 output x 8
+// input channels x 9 taps = 576 fp32 values that are 8 contiguous 288 B runs of the OIHW master weight.  It updates
+// them (same arithmetic as adamw_kernel), writes the parameter and both moments back, and emits the brick's part of the
+// forward operand ([src][tap][chunk][co][8]: 9 x 128 B) and of the 180-degree-rotated, in/out-swapped backward-data
+// operand ([tap'][chunk = o/8][co' = i][8 = o%8]: 9 x 128 B) from shared memory -- both sides coalesced.  Everything
+// that is not a packed conv weight (biases, the head conv) is updated by a few tail blocks from a list of 48-element rows.
+constexpr int kFusedMaxConvs = 64, kFusedMaxRows = 512, kFusedRow = 48, kFusedRowsPerBlock = 4;
+struct FusedConv {
+  long long w_off;            // element offset of the OIHW weight [48, I, 3, 3] in the parameter arena
+  int I, brick0;              // input channels (48 * sources); index of its first brick
+  __nv_bfloat16* fwd;         // forward operand
+  __nv_bfloat16* bwd[LV_MAX_SRC];   // backward-data operand per 48-channel source slice
+};
+struct FusedBatch {
+  FusedConv conv[kFusedMaxConvs];
+  // everything that is not a packed conv weight, cut into rows of <= 48 elements (4 rows per tail block: a serial
+  // loop over ~45 bias vectors in one block would cost ~1.5 us of memory latency each)
+  long long row_off[kFusedMaxRows];
+  short row_cnt[kFusedMaxRows];
+  int nconv, nrows, nbricks, brick_blocks;
+};
+
+__device__ __forceinline__ float adamw_one(float* p, const float* g, float* m, float* v, long long i, float lr, float b1,
+                                           float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  const float grad = g[i] * gscale;
+  float pv = p[i] * (1.f - lr * wd);
+  const float mv = m[i] + (grad - m[i]) * (1.f - b1);            // lerp_, as torch does
+  const float vv = v[i] * b2 + (1.f - b2) * grad * grad;
+  const float denom = sqrtf(vv) / bc2_sqrt + eps;
+  pv -= (lr / bc1) * (mv / denom);
+  p[i] = pv; m[i] = mv; v[i] = vv;
+  return pv;
+}
+
+__global__ void __launch_bounds__(192)
+adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  const __grid_constant__ FusedBatch fb, float lr, float b1, float b2, float eps, float wd, float bc1,
+                  float bc2_sqrt, float gscale) {
+  __shared__ float sm[8][72];   // [oo][ii*9 + tap]
+  const int t = threadIdx.x;
+  if (static_cast<int>(blockIdx.x) >= fb.brick_blocks) {   // biases, head conv, anything without a packed operand
+    const int row = (static_cast<int>(blockIdx.x) - fb.brick_blocks) * kFusedRowsPerBlock + t / kFusedRow;
+    const int i = t % kFusedRow;
+    if (row < fb.nrows && i < fb.row_cnt[row])
+      adamw_one(p, g, m, v, fb.row_off[row] + i, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    return;
+  }
+  for (int brick = blockIdx.x; brick < fb.nbricks; brick += fb.brick_blocks) {
+    int c = 0;
+    while (c + 1 < fb.nconv && fb.conv[c + 1].brick0 <= brick) ++c;
+    const FusedConv& cv = fb.conv[c];
+    const int ibricks = cv.I / 8;
+    const int local = brick - cv.brick0;
+    const int ob = local / ibricks, ib = local - ob * ibricks;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int e = t + 192 * r;                 // 0..575
+      const int oo = e / 72, rem = e - oo * 72;  // rem = ii*9 + tap: 72 contiguous floats of output channel 8*ob+oo
+      const long long idx = cv.w_off + (static_cast<long long>(8 * ob + oo) * cv.I + 8 * ib) * 9 + rem;
+      sm[oo][rem] = adamw_one(p, g, m, v, idx, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    }
+    __syncthreads();
+    const int s = ib / 6, chunk = ib - 6 * s;    // source slice and 8-channel chunk of the brick's input channels
+    if (t < 72) {
+      // forward operand: for tap, output channel 8*ob+oo: the 8 input channels of the brick
+      const int tap = t / 8, oo = t % 8;
+      uint4 q;
+      q.x = pack_bf16x2(sm[oo][0 * 9 + tap], sm[oo][1 * 9 + tap]);
+      q.y = pack_bf16x2(sm[oo][2 * 9 + tap], sm[oo][3 * 9 + tap]);
+      q.z = pack_bf16x2(sm[oo][4 * 9 + tap], sm[oo][5 * 9 + tap]);
+      q.w = pack_bf16x2(sm[oo][6 * 9 + tap], sm[oo][7 * 9 + tap]);
+      const size_t off = ((static_cast<size_t>(s * 9 + tap) * 6 + chunk) * 48 + 8 * ob + oo) * 8;
+      *reinterpret_cast<uint4*>(cv.fwd + off) = q;
+    } else if (t < 144) {
+      // backward-data operand of slice s: tap rotated, "output" channel = input channel 8*chunk+ii, the 8 = o%8
+      const int u = t - 72, tap = u / 8, ii = u % 8;
+      uint4 q;
+      q.x = pack_bf16x2(sm[0][ii * 9 + tap], sm[1][ii * 9 + tap]);
+      q.y = pack_bf16x2(sm[2][ii * 9 + tap], sm[3][ii * 9 + tap]);
+      q.z = pack_bf16x2(sm[4][ii * 9 + tap], sm[5][ii * 9 + tap]);
+      q.w = pack_bf16x2(sm[6][ii * 9 + tap], sm[7][ii * 9 + tap]);
+      const size_t off = ((static_cast<size_t>(8 - tap) * 6 + ob) * 48 + 8 * chunk + ii) * 8;
+      *reinterpret_cast<uint4*>(cv.bwd[s] + off) = q;
+    }
+  }
+}
+
+int adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs,
+                    int nconv, cudaStream_t stream) {
+  if (numel == 0) return LV_OK;
+  LV_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+  LV_CHECK_ARG(convs != nullptr && nconv >= 1 && nconv <= kFusedMaxConvs, "adamw+pack: 1..%d convs per call", kFusedMaxConvs);
+  static thread_local FusedBatch fb;
+  // convs must be sorted by offset and disjoint; everything between them becomes a plain range
+  long long pos = 0;
+  int nr = 0, bricks = 0;
+  for (int k = 0; k < nconv; ++k) {
+    const lv_fused_conv& c = convs[k];
+    LV_CHECK_ARG(c.cout == 48 && c.cin_total % 48 == 0 && c.cin_total >= 48 && c.cin_total <= 48 * LV_MAX_SRC,
+                 "adamw+pack: conv %d must be 48 x (48*k) x 3 x 3", k);
+    LV_CHECK_ARG(c.w_off >= pos && c.w_off + 48ll * c.cin_total * 9 <= numel, "adamw+pack: conv %d out of order / range", k);
+    LV_CHECK_ARG(c.fwd != nullptr, "adamw+pack: conv %d has no forward operand", k);
+    for (long long q = pos; q < c.w_off; q += kFusedRow) {
+      LV_CHECK_ARG(nr < kFusedMaxRows, "adamw+pack: too many parameters outside the packed convs");
+      fb.row_off[nr] = q;
+      fb.row_cnt[nr] = static_cast<short>(c.w_off - q < kFusedRow ? c.w_off - q : kFusedRow);
+      ++nr;
+    }
+    fb.conv[k].w_off = c.w_off;
+    fb.conv[k].I = c.cin_total;
+    fb.conv[k].brick0 = bricks;
+    fb.conv[k].fwd = static_cast<__nv_bfloat16*>(c.fwd);
+    for (int sidx = 0; sidx < LV_MAX_SRC; ++sidx) {
+      fb.conv[k].bwd[sidx] = static_cast<__nv_bfloat16*>(c.bwd[sidx]);
+      LV_CHECK_ARG(sidx >= c.cin_total / 48 || c.bwd[sidx] != nullptr, "adamw+pack: conv %d lacks a backward operand", k);
+    }
+    bricks += 6 * (c.cin_total / 8);
+    pos = c.w_off + 48ll * c.cin_total * 9;
+  }
+  for (long long q = pos; q < numel; q += kFusedRow) {
+    LV_CHECK_ARG(nr < kFusedMaxRows, "adamw+pack: too many parameters outside the packed convs");
+    fb.row_off[nr] = q;
+    fb.row_cnt[nr] = static_cast<short>(numel - q < kFusedRow ? numel - q : kFusedRow);
+    ++nr;
+  }
+  fb.nconv = nconv; fb.nrows = nr; fb.nbricks = bricks;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  fb.brick_blocks = bricks < 148 * 8 ? bricks : 148 * 8;
+  const int tail_blocks = (nr + kFusedRowsPerBlock - 1) / kFusedRowsPerBlock;
+  adamw_pack_kernel<<<fb.brick_blocks + tail_blocks, 192, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, fb, lr, beta1, beta2, eps, weight_decay,
+                                                  static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
 }  // namespace lv

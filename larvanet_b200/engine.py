@@ -200,6 +200,14 @@ class LarvaEngine:
                 items_b.append(dict(w=w, packed=self._pk[(prefix, 'bwd', s)], transpose=1, i_off=C * s, i_cnt=C, cin=C,
                                     dtype=dt))
         self._pack_items_fwd, self._pack_items_bwd = items_f, items_b
+        # the optimizer can update the weights and emit both operand forms in ONE kernel (bf16, 48-output convs only)
+        self._fused_convs = None
+        if dt == torch.bfloat16 and os.environ.get('LARVANET_B200_FUSED_ADAMW', '1') != '0' and len(self._conv_layers) <= 64 \
+                and all(O == C and I % C == 0 and I // C <= 4 for _, O, I in self._conv_layers):
+            convs = [dict(w_off=self.arena.offsets[prefix + '.weight'][0], cin_total=I, fwd=self._pk[(prefix, 'fwd')],
+                          bwd=[self._pk[(prefix, 'bwd', s)] for s in range(I // C)]) for prefix, O, I in self._conv_layers]
+            convs.sort(key=lambda c: c['w_off'])
+            self._fused_convs = ops.build_fused_convs(convs)
         # marshalled once: re-packing runs every optimizer step and must not cost host time per layer
         self._pack_arr_fwd = ops.build_pack_arrays(items_f)
         self._pack_arr_all = ops.build_pack_arrays(items_f + items_b)
@@ -215,6 +223,14 @@ class LarvaEngine:
 
     def mark_weights_changed(self):
         self._packed_version = None
+
+    def fused_update_available(self):
+        return self._fused_convs is not None and not self.simt
+
+    def weights_updated_and_packed(self):
+        """Called by FusedAdamW after lv_adamw_pack_step: both operand forms are current."""
+        self._packed_version = self.arena.version()
+        self._packed_bwd = True
 
     def weights_updated(self):
         """Called by FusedAdamW right after its update kernel: re-pack NOW, on the same stream, in the form the last

@@ -303,6 +303,30 @@ def l1_loss_grad(out_hr, truth_hr, loss_sum, grad_sign=None):
                                       n, c, h4 // 4, w4 // 4, dt, _stream()), 'lv_l1_loss_grad')
 
 
+def build_fused_convs(convs):
+    """convs: list of dicts(w_off, cin_total, fwd=packed tensor, bwd=[packed tensor per 48-channel slice]) sorted by
+    w_off -> (ctypes FusedConv array, count) for adamw_pack_step.  The tensors must stay alive."""
+    arr = (_lib.FusedConv * len(convs))()
+    for k, c in enumerate(convs):
+        arr[k].w_off = int(c['w_off'])
+        arr[k].cout = 48
+        arr[k].cin_total = int(c['cin_total'])
+        arr[k].fwd = _ptr(c['fwd'], None, 'fwd')
+        for s, t in enumerate(c['bwd']):
+            arr[k].bwd[s] = _ptr(t, None, 'bwd')
+    return arr, len(convs)
+
+
+def adamw_pack_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, fused, grad_scale=1.0):
+    """AdamW over the whole arena + re-pack of the listed convs' forward / backward-data operands, one launch."""
+    arr, cnt = fused
+    check(_lib.load().lv_adamw_pack_step(_ptr(param, torch.float32, 'param'), _ptr(grad, torch.float32, 'grad'),
+                                         _ptr(exp_avg, torch.float32, 'exp_avg'), _ptr(exp_avg_sq, torch.float32, 'exp_avg_sq'),
+                                         param.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                         float(weight_decay), int(step), float(grad_scale), arr, cnt, _stream()),
+          'lv_adamw_pack_step')
+
+
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
     check(_lib.load().lv_adamw_step(_ptr(param, torch.float32, 'param'), _ptr(grad, torch.float32, 'grad'),
                                     _ptr(exp_avg, torch.float32, 'exp_avg'), _ptr(exp_avg_sq, torch.float32, 'exp_avg_sq'),

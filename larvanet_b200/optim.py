@@ -48,6 +48,12 @@ class FusedAdamW(torch.optim.AdamW):
         g = self.param_groups[0]
         self._steps += 1
         a = self._engine.arena
+        if getattr(self._engine, 'fused_update_available', lambda: False)():
+            # update + re-pack of the conv operands (forward and backward-data forms) in one kernel
+            ops.adamw_pack_step(a.flat, a.grad, self._exp_avg, self._exp_avg_sq, g['lr'], g['betas'][0], g['betas'][1],
+                                g['eps'], g['weight_decay'], self._steps, self._engine._fused_convs, 1.0)
+            self._engine.weights_updated_and_packed()
+            return
         ops.adamw_step(a.flat, a.grad, self._exp_avg, self._exp_avg_sq, g['lr'], g['betas'][0], g['betas'][1], g['eps'],
                        g['weight_decay'], self._steps, 1.0)
         if hasattr(self._engine, 'weights_updated'):

@@ -303,3 +303,39 @@ def test_device_prefetcher_feeds_identical_batches():
     assert len(got) == len(host)
     for (x, t), (hx, ht) in zip(got, host):
         assert torch.equal(x.cpu(), hx) and torch.equal(t.cpu(), ht)
+
+
+def test_fused_adamw_pack_equals_separate_kernels(golden_dir):
+    """lv_adamw_pack_step == lv_adamw_step followed by lv_pack_conv3x3_weights, bit for bit (parameters, both moments,
+    forward and backward-data operands), for LarvaNet and for LarvaNetV2 (4-source merge conv)."""
+    from larvanet_b200 import ops
+    for name in ('larvanet_m2_b21', 'larvanetv2_m4_b1111'):
+        g, v2, blocks, params, lr, hr = _case(golden_dir, name)
+        m = _make(v2, blocks, 'bf16', training=True)
+        load_params(m.get_model(), params)
+        eng = m._engine()
+        assert eng.fused_update_available()
+        eng.train_step(torch.from_numpy(lr).cuda(), torch.from_numpy(hr).cuda())       # real gradients, operands packed
+        a = eng.arena
+        gen = torch.Generator(device='cuda').manual_seed(1)
+        m0 = torch.randn(a.flat.shape, device='cuda', generator=gen) * 1e-3
+        v0 = torch.rand(a.flat.shape, device='cuda', generator=gen) * 1e-6
+        p0 = a.flat.clone()
+        hyp = dict(lr=3e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, step=7)
+        # separate kernels
+        p1, m1, v1 = p0.clone(), m0.clone(), v0.clone()
+        a.flat.copy_(p1)
+        ops.adamw_step(a.flat, a.grad, m1, v1, hyp['lr'], hyp['beta1'], hyp['beta2'], hyp['eps'], hyp['weight_decay'], hyp['step'])
+        eng.repack(backward=True, force=True)
+        torch.cuda.synchronize()
+        p_sep, packed_sep = a.flat.clone(), eng._packed.clone()
+        # fused kernel, from the same state
+        a.flat.copy_(p0)
+        eng._packed.zero_()
+        m2, v2_ = m0.clone(), v0.clone()
+        ops.adamw_pack_step(a.flat, a.grad, m2, v2_, hyp['lr'], hyp['beta1'], hyp['beta2'], hyp['eps'], hyp['weight_decay'],
+                            hyp['step'], eng._fused_convs)
+        torch.cuda.synchronize()
+        assert torch.equal(a.flat, p_sep), name
+        assert torch.equal(m2, m1) and torch.equal(v2_, v1), name
+        assert torch.equal(eng._packed, packed_sep), name
