@@ -88,7 +88,9 @@ class SymmetricGradExchange:
                 torch.cuda.synchronize(device)
             except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", agreed on collectively below
                 ok, ex = 0, None
-                print(f'[larvanet_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL')
+                import sys
+                print(f'[larvanet_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL',
+                      file=sys.stderr)
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         return ex if int(flag.item()) == 1 else None
