@@ -222,8 +222,10 @@ typedef struct lv_fused_conv {
   void* bwd[LV_MAX_SRC];
 } lv_fused_conv;
 
-/* lv_adamw_step + lv_pack_conv3x3_weights (forward and backward-data operands) of the listed convs in ONE kernel; `convs`
- * is a HOST array (<= 64, sorted by w_off, disjoint); parameters outside the listed weights get the plain update. */
+/* optim.AdamW.step() (models/LarvaNet.py:86-88,114; models/LarvaNetV2.py:83-85) for the whole parameter arena AND the
+ * re-pack of the listed convs' operands (= lv_adamw_step + lv_pack_conv3x3_weights, forward and backward-data forms) in
+ * ONE kernel; `convs` is a HOST array (<= 64, sorted by w_off, disjoint); parameters outside the listed weights get the
+ * plain update.  Bit-identical to the two separate calls. */
 int lv_adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                        float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                        const lv_fused_conv* convs, int nconv, void* stream);
