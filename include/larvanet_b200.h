@@ -222,7 +222,7 @@ typedef struct lv_fused_conv {
   void* bwd[LV_MAX_SRC];
 } lv_fused_conv;
 
-/* optim.AdamW.step() (models/LarvaNet.py:86-88,114; models/LarvaNetV2.py:83-85) for the whole parameter arena AND the
+/* optim.AdamW.step() (models/LarvaNet.py:86-88,114; models/LarvaNetV2.py:83-85,123) for the whole parameter arena AND the
  * re-pack of the listed convs' operands (= lv_adamw_step + lv_pack_conv3x3_weights, forward and backward-data forms) in
  * ONE kernel; `convs` is a HOST array (<= 64, sorted by w_off, disjoint); parameters outside the listed weights get the
  * plain update.  Bit-identical to the two separate calls. */
