@@ -65,3 +65,27 @@ def test_sharding_helpers():
     assert lvdist.shard_range(2, 3, 4) == (2, 2)
     assert lvdist.frames_for_rank(7, 1, 3) == [1, 4]
     assert lvdist.grad_scale(100, 4, 5) == 1.0 / 2000.0
+
+
+def _symm_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    lvdist.init_from_env('gloo')
+    # no CUDA here: creating the symmetric allocation fails on every rank, the ranks AGREE on that through the MIN
+    # all-reduce and everybody keeps the plain all-reduce path (nobody may end up alone in a collective)
+    ex = lvdist.SymmetricGradExchange.try_create(1000, torch.device('cpu'))
+    flat = torch.full((8,), float(rank + 1), dtype=torch.float32)
+    for wk in lvdist.allreduce_gradients(flat):
+        wk.wait()
+    if rank == 0:
+        np.savez(out_path, none=np.array([ex is None]), flat=flat.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_symmetric_exchange_falls_back_collectively(tmp_path):
+    out = str(tmp_path / 'symm.npz')
+    mp.spawn(_symm_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    assert bool(got['none'][0])
+    np.testing.assert_array_equal(got['flat'], np.full(8, 3.0, dtype=np.float32))
