@@ -378,14 +378,16 @@ def steady_state_chain(dev, peak_burst):
     x = torch.randn((n, h, 6, w, 8), device=dev, generator=g).to(torch.bfloat16)
     wt = torch.randn((48, 48, 3, 3), device=dev, generator=g) * 0.05
     b = torch.zeros(48, device=dev)
+    from larvanet_b200 import _lib
+    wl = _lib.LV_W_KY_STACKED      # what the engines use at this size (LarvaEngine.use_row_path): the row-marching chain
     packed = torch.zeros(ops.packed_weight_bytes(48, 48, torch.bfloat16), dtype=torch.uint8, device=dev)
-    ops.pack_weights([dict(w=wt, packed=packed, cin=48, dtype=torch.bfloat16)])
+    ops.pack_weights([dict(w=wt, packed=packed, cin=48, dtype=torch.bfloat16, wlayout=wl)])
     bufs = [torch.empty_like(x), torch.empty_like(x)]
     args, src = [], x
     for i in range(layers):
         dst = bufs[i & 1]
         args.append(ops.make_conv_args([src], packed, 48, bias=b, out=dst, relu=(i & 1) == 0,
-                                       res1=None if (i & 1) == 0 else x))
+                                       res1=None if (i & 1) == 0 else x, wlayout=wl))
         src = dst
     ws = ops.chain_workspace(n, h, w, dev)
     for _ in range(2):
@@ -400,6 +402,7 @@ def steady_state_chain(dev, peak_burst):
     sec = e0.elapsed_time(e1) * 1e-3 / 5
     ach = 2.0 * 9 * 48 * 48 * n * h * w * layers / sec / 1e12
     return {'workload': f'{layers} chained 48->48 convs on {n} x {h}x{w} px (activations 100 MB per layer: HBM-resident)',
+            'kernel': 'row::conv3x3_row_kernel<48,48> (row-marching, ky-stacked N=144 MMAs; csrc/conv_row.cu)',
             'achieved': ach, 'peak': peak_burst, 'unit': 'TFLOP/s', 'frac': ach / peak_burst, 'us_per_layer': sec / layers * 1e6,
             'peak_source': 'measured burst bf16 (kernel timed alone)'}
 

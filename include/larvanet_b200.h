@@ -234,6 +234,24 @@ int lv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                   void* stream);
 
+/*
+ * Data-parallel optimizer step (new capability; the reference is single-process): the SUM all-reduce of the
+ * gradient arena, optim.AdamW.step() (models/LarvaNet.py:86-88,114) and the operand re-pack of lv_adamw_pack_step in ONE
+ * kernel.  Every rank's gradient arena, flag block and loss accumulator live in peer-mapped (symmetric) memory:
+ *   peer_grads[r]  fp32 [numel]      gradient arena of rank r as mapped on THIS device (index = rank, own entry included)
+ *   peer_flags[r]  uint32 [32]       zero-initialised flag block of rank r (device-side barriers, slot per writer rank)
+ *   peer_loss[r]   double [1]        rank r's local loss accumulator; *loss_out (local) receives the sum over ranks
+ *   ctl            uint32 [4]        zero-initialised device-LOCAL control words of this rank
+ * The kernel waits (device side, over NVLink) until every rank has reached it -- i.e. all gradients are complete --, reads
+ * the gradients of all ranks in rank order (bit-identical sums on every rank), and returns only when every rank is done
+ * reading, so the caller may overwrite its arena right after.  Every rank must call it the same number of times.
+ * world must be 2, 4 or 8; `host` arrays are read during the call only.
+ */
+int lv_dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs, int nconv,
+                          const void* const* peer_grads, void* const* peer_flags, const void* const* peer_loss,
+                          double* loss_out, uint32_t* ctl, int world, int rank, void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t lv_launch_count(void);
 

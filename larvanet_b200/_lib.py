@@ -88,6 +88,9 @@ SIGNATURES = {
     'lv_adamw_pack_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float,
                                                                                       C.POINTER(FusedConv), C.c_int, C.c_void_p]),
     'lv_adamw_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_void_p]),
+    'lv_dp_adamw_pack_step': (C.c_int, [C.c_void_p] * 3 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float,
+                                                                                         C.POINTER(FusedConv), C.c_int] +
+                              [C.POINTER(C.c_void_p)] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'lv_launch_count': (C.c_int64, []),
 }
 

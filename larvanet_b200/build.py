@@ -18,7 +18,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(CSRC, 'build')
 LIB = os.path.join(HERE, 'liblarvanet_b200.so')
-SOURCES = ['capi.cu', 'conv_tc.cu', 'conv_tc_ky.cu', 'conv_chain.cu', 'conv_strip.cu', 'conv_simt.cu', 'wgrad.cu', 'head.cu', 'layout.cu']
+SOURCES = ['capi.cu', 'conv_tc.cu', 'conv_row.cu', 'conv_chain.cu', 'conv_simt.cu', 'wgrad.cu', 'head.cu', 'layout.cu']
+# measured-slower experiments of round 1 (cluster-resident strips, ky-stacked tiles with a shuffle epilogue) live in
+# tools/experiments/ and are only compiled into the library with LARVANET_B200_EXPERIMENTAL=1 (adds -DLV_EXPERIMENTAL)
+EXPERIMENTAL = os.environ.get('LARVANET_B200_EXPERIMENTAL', '0') == '1'
+EXPERIMENT_DIR = os.path.join(os.path.dirname(HERE), 'tools', 'experiments')
+EXPERIMENT_SOURCES = ['conv_strip.cu', 'conv_tc_ky.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
 
@@ -43,16 +48,25 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
     headers.append(os.path.join(os.path.dirname(HERE), 'include', 'larvanet_b200.h'))
     objs, jobs = [], []
-    for src in SOURCES:
-        s = os.path.join(CSRC, src)
-        o = os.path.join(BUILD, src.replace('.cu', '.o'))
+    flags = list(NVCC_FLAGS)
+    tag = ''
+    sources = [os.path.join(CSRC, f) for f in SOURCES]
+    if EXPERIMENTAL:
+        flags += ['-DLV_EXPERIMENTAL', '-I', CSRC]
+        tag = '.exp'                       # separate objects: the flag changes capi.cu / conv_chain.cu
+        sources += [os.path.join(EXPERIMENT_DIR, f) for f in EXPERIMENT_SOURCES]
+    for s in sources:
+        o = os.path.join(BUILD, os.path.basename(s).replace('.cu', tag + '.o'))
         objs.append(o)
         if force or _stale(o, [s] + headers):
             jobs.append((s, o))
+    marker = os.path.join(BUILD, 'flavour.txt')
+    flavour = 'experimental' if EXPERIMENTAL else 'product'
+    relink = not os.path.exists(marker) or open(marker).read() != flavour
 
     def compile_one(job):
         s, o = job
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', s, '-o', o]
+        cmd = [nvcc] + flags + ['-c', s, '-o', o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return s, r
 
@@ -68,12 +82,14 @@ def build(force=False, verbose=False):
     if jobs:
         with open(os.path.join(BUILD, 'ptxas.log'), 'w') as f:
             f.write('\n'.join(logs))
-    if force or jobs or not os.path.exists(LIB):
+    if force or jobs or relink or not os.path.exists(LIB):
         cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stderr)
             raise RuntimeError('link failed')
+        with open(marker, 'w') as f:
+            f.write(flavour)
     return LIB
 
 

@@ -35,7 +35,13 @@ int sm_count() {
 
 // implemented in the other translation units
 int conv3x3_tc(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
+#ifdef LV_EXPERIMENTAL
 int conv3x3_tc_ky(const lv_conv_args& a, int max_ctas, cudaStream_t stream);
+#endif
+bool conv3x3_row_supported(const lv_conv_args& a);
+long long conv3x3_row_workspace_bytes(int n, int h, int w);
+int conv3x3_row_chain(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
+                      cudaStream_t stream);
 int conv3x3_simt(const lv_conv_args& a, cudaStream_t stream);
 long long conv3x3_chain_workspace_bytes(int n, int h, int w);
 int conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
@@ -56,6 +62,8 @@ int image_to_uint8(const float*, uint8_t*, long long, cudaStream_t);
 int adamw_pack_step(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float,
                     const lv_fused_conv*, int, cudaStream_t);
 int psnr_sqsum(const float*, const float*, double*, int, int, int, int, int, cudaStream_t);
+int dp_adamw_pack_step(float*, float*, float*, long long, float, float, float, float, float, int, float, const lv_fused_conv*, int,
+                       const void* const*, void* const*, const void* const*, double*, uint32_t*, int, int, cudaStream_t);
 long long wgrad_workspace_bytes(const lv_wgrad_item*, int, int);
 int wgrad(const lv_wgrad_item*, const lv_wgrad_item*, int, int, void*, cudaStream_t);
 int wgrad_simt(const lv_wgrad_item*, const lv_wgrad_item*, int, int, cudaStream_t);
@@ -137,7 +145,18 @@ int lv_conv3x3(const lv_conv_args* a, int max_ctas, void* stream) {
   if (rc != LV_OK) return rc;
   if (a->dtype == LV_BF16) {
     LV_CHECK_ARG(a->cin % 16 == 0, "conv3x3: the tensor-core path needs cin %% 16 == 0 (got %d)", a->cin);
-    if (a->wlayout == LV_W_KY_STACKED) return conv3x3_tc_ky(*a, max_ctas, static_cast<cudaStream_t>(stream));
+    if (a->wlayout == LV_W_KY_STACKED) {
+      // row-marching kernel (conv_row.cu): 9 MMAs of N = 3*cout per 128 pixels, vertical taps summed in TMEM
+      if (conv3x3_row_supported(*a)) return conv3x3_row_chain(a, 1, nullptr, 0, max_ctas, static_cast<cudaStream_t>(stream));
+#ifdef LV_EXPERIMENTAL
+      return conv3x3_tc_ky(*a, max_ctas, static_cast<cudaStream_t>(stream));
+#else
+      set_error("conv3x3: ky-stacked weights are only supported for single-source bf16 48->48 / 64->64 convs "
+                "(EPI_NHWC, or EPI_PS4 at 48 channels); got cin=%d x %d sources, cout=%d, epilogue %d",
+                a->cin, a->num_src, a->cout, a->epilogue);
+      return LV_ERR_INVALID;
+#endif
+    }
     return conv3x3_tc(*a, max_ctas, static_cast<cudaStream_t>(stream));
   }
   return conv3x3_simt(*a, static_cast<cudaStream_t>(stream));
@@ -145,7 +164,8 @@ int lv_conv3x3(const lv_conv_args* a, int max_ctas, void* stream) {
 
 int64_t lv_conv_chain_workspace_bytes(int n, int h, int w) {
   if (n < 0 || h < 0 || w < 0) return -1;
-  return conv3x3_chain_workspace_bytes(n, h, w);
+  const long long a = conv3x3_chain_workspace_bytes(n, h, w), b = conv3x3_row_workspace_bytes(n, h, w);
+  return a > b ? a : b;   // one workspace serves both chain kernels (tile flags / row-job flags)
 }
 
 int lv_conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, int64_t sync_ws_bytes, int max_ctas,
@@ -157,6 +177,8 @@ int lv_conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, int64
     LV_CHECK_ARG(layers[i].bias == nullptr || (reinterpret_cast<uintptr_t>(layers[i].bias) & 15u) == 0,
                  "conv chain: layer %d bias is not 16-byte aligned", i);
   }
+  if (layers[0].wlayout == LV_W_KY_STACKED)
+    return conv3x3_row_chain(layers, count, sync_ws, sync_ws_bytes, max_ctas, static_cast<cudaStream_t>(stream));
   return conv3x3_chain(layers, count, sync_ws, sync_ws_bytes, max_ctas, static_cast<cudaStream_t>(stream));
 }
 
@@ -221,6 +243,16 @@ int lv_adamw_pack_step(float* param, const float* grad, float* exp_avg, float* e
   LV_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adamw+pack: null pointer");
   return adamw_pack_step(param, grad, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
                          convs, nconv, static_cast<cudaStream_t>(stream));
+}
+
+int lv_dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs, int nconv,
+                          const void* const* peer_grads, void* const* peer_flags, const void* const* peer_loss,
+                          double* loss_out, uint32_t* ctl, int world, int rank, void* stream) {
+  LV_CHECK_ARG(param && exp_avg && exp_avg_sq, "dp adamw+pack: null pointer");
+  return dp_adamw_pack_step(param, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, grad_scale, convs,
+                            nconv, peer_grads, peer_flags, peer_loss, loss_out, ctl, world, rank,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int lv_image_to_uint8(const float* src, uint8_t* dst, int64_t numel, void* stream) {

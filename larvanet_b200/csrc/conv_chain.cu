@@ -467,7 +467,9 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
 
 }  // namespace chain
 
+#ifdef LV_EXPERIMENTAL
 int conv3x3_strip(const lv_conv_args* layers, int count, cudaStream_t stream);
+#endif
 
 long long conv3x3_chain_workspace_bytes(int n, int h, int w) {
   const long long tiles = static_cast<long long>(n) * ((h + chain::kTileH - 1) / chain::kTileH) * ((w + chain::kTileW - 1) / chain::kTileW);
@@ -501,18 +503,32 @@ int conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, long lon
                sync_ws_bytes, (tt + 1) * 4);
   g.total_tiles = static_cast<int>(tt);
 
-  // small images (patch training): one cluster per image, activations resident in shared memory (conv_strip.cu)
+#ifdef LV_EXPERIMENTAL
+  // small images (patch training): one cluster per image, activations resident in shared memory
+  // (tools/experiments/conv_strip.cu, opt-in at run time with LARVANET_B200_STRIP=1)
   if (static_cast<long long>(a0.n) * a0.h * a0.w > 0) {
     const int rc = conv3x3_strip(layers, count, stream);
     if (rc != 1) return rc;
   }
+#endif
   static thread_local chain::Params params;   // staging only; the launch copies it by value
   for (int i = 0; i < count; ++i) params.layer[i] = layers[i];
   auto kern = chain::conv3x3_chain_kernel<48, 48, 4>;
-  static bool configured = false;
-  if (!configured) {
+  // once per DEVICE: opt into the dynamic shared memory and make sure one CTA per SM can really be resident -- the
+  // data-flow waits need every CTA of the grid running at the same time
+  static bool configured[64] = {false};
+  int dev = 0;
+  LV_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!configured[dev]) {
     LV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(C_::smem_bytes())));
-    configured = true;
+    int per_sm = 0;
+    LV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, chain::kThreads, C_::smem_bytes()));
+    if (per_sm < 1) {
+      set_error("conv chain: a CTA (%zu B shared memory) does not fit on an SM of device %d", C_::smem_bytes(), dev);
+      return LV_ERR_UNSUPPORTED;
+    }
+    configured[dev] = true;
   }
   long long ctas = max_ctas > 0 ? max_ctas : sm_count();
   if (ctas > sm_count()) ctas = sm_count();   // one resident CTA per SM: the data-flow waits need every CTA running

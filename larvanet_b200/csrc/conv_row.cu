@@ -1,0 +1,638 @@
+// Row-marching 3x3 convolution on the sm_100a tensor cores: one layer or a whole chain of layers per persistent launch.
+//
+// Why a second conv kernel: conv_tc.cu / conv_chain.cu issue 27 MMAs of N = 48 per 128-pixel tile (one per tap and 16-channel
+// K step).  An M=128, K=16 SS MMA costs max(N/2, 32 + N/4) clk (profiles/r01_umma_microbench.txt): at N = 48 that is 45 clk,
+// of which 32 are the 4 KB A-tile read from shared memory and only 24 tensor-pipe work -- the tile is shared-memory bound
+// at a 53 % tensor ceiling because every input pixel is read NINE times.  Here every input pixel is read THREE times:
+//
+//   * M = 128 consecutive pixels of ONE image row ("strip").  The batch's rows are laid on a line with one zero pad pixel
+//     between images (pitch W+1; the pad is the left AND right zero padding of the two images it separates), so 48-px
+//     training patches fill the 128 lanes as well as 480-px frames do.
+//   * B = the three vertical taps stacked along N (LV_W_KY_STACKED: [kx][cin/8][ky*cout + co][8], N = 3*cout = 144): the
+//     MMAs of INPUT row y produce, side by side in TMEM, its contributions to OUTPUT rows y+1 (ky=0), y (ky=1), y-1 (ky=2).
+//   * The accumulators of the output rows live in a ring of TMEM column blocks (10 x 48 or 8 x 64 columns), consecutive
+//     rows in ADJACENT blocks in descending column order.  The N=144 MMA of input row y therefore lands on the blocks of
+//     rows y+1, y, y-1 at once and the sum over the vertical taps happens inside the tensor core: no shuffle epilogue
+//     (conv_tc_ky.cu's problem), 9 MMAs of 73 clk per row (tensor bound) instead of 27 of 45.  An output row is complete --
+//     and drained by an epilogue group while the MMA warp marches on -- once input row y+1 has been issued.
+//     The first MMA that touches a block must overwrite, the others accumulate; the flag is per instruction, so the first
+//     (kx=0, k-step 0) MMA of a row is split in two (N=48 overwrite + N=96 accumulate), as are MMAs at the ring's wrap.
+//
+// Work unit ("job") = one strip x `rows_per_job` rows; a job of R rows reads R+2 input rows, each ONCE, through a ring of
+// row buffers ([8-channel chunk][130 px][16 B] = the SWIZZLE_NONE K-major A operand; the horizontal tap is a 16-byte shift of
+// the descriptor start).  Jobs of one layer are dealt round-robin to the persistent CTAs (one per SM).
+//
+// Chains (count > 1): same data-flow protocol as conv_chain.cu -- done[job] counts finished layers, a job of layer l
+// starts when its 3x3 job neighbourhood has finished layer l-1, a publisher warp turns "all rows of the job stored" into
+// one red.release.gpu; next-layer weights are prefetched into a shared-memory ring.
+//
+// Epilogues are the chain kernels' (chain_epilogue.cuh): one pixel x NT channels per thread straight from TMEM to
+// global memory; a warp writes 32 consecutive pixels = 512 contiguous bytes per 8-channel chunk.
+#include "chain_epilogue.cuh"
+#include "conv_epilogue.cuh"
+#include "lv_common.cuh"
+
+namespace lv {
+
+extern int g_use_pdl;
+
+namespace row {
+
+constexpr int kMaxLayers = 96;   // LV_CHAIN_MAX_LAYERS
+constexpr int kLanes = 128, kRowPx = kLanes + 2;
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 64;
+constexpr int kMmaWarp = kEpiWarps;
+constexpr int kPubWarp = kMmaWarp + 1 + kProdThreads / 32;
+constexpr int kThreads = kEpiThreads + 32 + kProdThreads + 32;   // 384
+
+struct Params {
+  lv_conv_args layer[kMaxLayers];
+};
+
+struct Geom {
+  int N, H, W, P;           // P = W + 1: pitch of one image on the line
+  int nstrips, rows_per_job, nblocks, total_jobs;
+};
+
+template <int CIN, int NT, int NSTAGE, int WBUFS>
+struct Cfg {
+  static constexpr int CH = CIN / 8;
+  static constexpr int KSTEPS = CIN / 16;
+  static constexpr int N3 = 3 * NT;
+  static constexpr int A_PLANE = kRowPx * 16;        // 2080 B: one 8-channel chunk of a row buffer
+  static constexpr int A_STAGE = CH * A_PLANE;
+  static constexpr int W_PLANE = N3 * 16;            // one 8-channel chunk of one kx block of the weights
+  static constexpr int W_KX = CH * W_PLANE;
+  static constexpr int W_LAYER = 3 * W_KX;
+  static constexpr int RING = (512 / NT) & ~1;       // accumulator blocks (even: block parity == epilogue group)
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int PIECES = (kRowPx * CH + kProdThreads - 1) / kProdThreads;
+  static constexpr int NBARS = 2 * NSTAGE + 2 * RING + 2 * WBUFS + 4;
+  static constexpr size_t smem_bytes() {
+    return static_cast<size_t>(WBUFS) * W_LAYER + static_cast<size_t>(NSTAGE) * A_STAGE + NBARS * 8 + 64;
+  }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// poll relaxed, finish with one acquire (an acquire load invalidates the SM's L1, see conv_chain.cu)
+__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t need) {
+  if (ld_acquire_gpu(p) >= need) return;
+  uint32_t spins = 0;
+  while (ld_relaxed_gpu(p) < need) {
+    __nanosleep(32);
+    if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+  }
+  (void)ld_acquire_gpu(p);
+}
+
+// runtime-N instruction descriptor (M = 128, bf16 x bf16 -> fp32, both operands K-major)
+__device__ __forceinline__ uint32_t idesc_n(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+struct Job {
+  int u, y0, y1;
+};
+
+struct EpiCtx {
+  Geom g;
+  const uint32_t* done;
+  volatile uint32_t* pub_seen;
+  uint32_t tfull0, tempty0, pub_bar0, tmem_lane;   // barrier ring bases, TMEM address of this warp's lane quarter
+  int G, lane, eg, m, nlayers;
+  size_t chunk_stride, row_stride;
+};
+
+constexpr int kKindPs4 = 100, kKindGeneric = -1;
+
+// All jobs of one layer for one epilogue thread (one line position = one pixel column of the strip).
+template <int KIND, int NT, int RING>
+__device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_args& a, int l, int first, uint32_t k) {
+  constexpr int NCH = NT / 8;
+  const bool has_ops = (a.mask != nullptr) || (a.res1 != nullptr) || (a.res2 != nullptr);
+  chain::FastEpi fe;
+  fe.mask = reinterpret_cast<const __nv_bfloat16*>(a.mask);
+  fe.res1 = reinterpret_cast<const __nv_bfloat16*>(a.res1);
+  fe.res2 = reinterpret_cast<const __nv_bfloat16*>(a.res2);
+  fe.out = reinterpret_cast<__nv_bfloat16*>(a.out);
+  fe.res_scale = a.res_scale;
+  fe.relu = a.relu;
+  float loss = 0.f;
+  constexpr bool kBiasRegs = (NT <= 48) && (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 4);
+  float breg[kBiasRegs ? NT : 1];
+  const float* bias_g = a.bias;
+  if constexpr (kBiasRegs) {
+#pragma unroll
+    for (int i = 0; i < NT / 4; ++i) {
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + i);
+      breg[4 * i] = b4.x; breg[4 * i + 1] = b4.y; breg[4 * i + 2] = b4.z; breg[4 * i + 3] = b4.w;
+    }
+  }
+  for (int job = first; job < cx.g.total_jobs; job += cx.G) {
+    const int bk = job / cx.g.nstrips, u = job - bk * cx.g.nstrips;
+    const int y0 = bk * cx.g.rows_per_job;
+    const int y1 = min(cx.g.H, y0 + cx.g.rows_per_job);
+    const int p = u * kLanes + cx.m;
+    const int n = p / cx.g.P, x = p - n * cx.g.P;
+    const bool valid = (n < cx.g.N) && (x < cx.g.W);
+    const size_t o_img = valid ? act_off(n, 0, x, 0, cx.g.H, cx.g.W, NCH) : 0;
+    if (l > 0 && (KIND == kKindGeneric || has_ops)) {
+      // same-position operands come from earlier layers of this chain, possibly written by another CTA
+      if (cx.lane == 0) wait_flag(cx.done + job, static_cast<uint32_t>(l));
+      __syncwarp();
+    }
+    for (int yo = y0; yo < y1; ++yo) {
+      const uint32_t kk = k + static_cast<uint32_t>(yo - y0);
+      if ((kk & 1u) != static_cast<uint32_t>(cx.eg)) continue;
+      const uint32_t blk = kk % RING;
+      const uint32_t par = (kk / RING) & 1u;
+      const uint32_t taddr = cx.tmem_lane + (RING - 1 - blk) * NT;
+      const uint32_t tfull = cx.tfull0 + 8u * blk, tempty = cx.tempty0 + 8u * blk;
+      const size_t o0 = o_img + static_cast<size_t>(yo) * cx.row_stride;
+      const uint32_t seen = (cx.nlayers > 1) ? *cx.pub_seen : 0u;
+      if constexpr (KIND == kKindPs4) {
+        loss += chain::ps4_tile<NT>(a, bias_g, valid, n, yo, x, cx.g.H, cx.g.W, o0, cx.chunk_stride, taddr, tfull, tempty, par);
+      } else if constexpr (KIND == kKindGeneric) {
+        mbar_wait_relaxed(tfull, par);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int j = 0; j < NT / 16; ++j) {
+          float v[16];
+          tmem_ld16(taddr + j * 16, v);
+          tmem_ld_wait();
+          if (valid) loss += conv_epilogue16<__nv_bfloat16>(a, n, yo, x, j * 16, v);
+        }
+        tc_fence_before_sync();
+        mbar_arrive(tempty);
+      } else {
+        chain::fast_tile<KIND, NT, kBiasRegs>(fe, breg, bias_g, valid, o0, cx.chunk_stride, taddr, tfull, tempty, par);
+      }
+      if (cx.nlayers > 1) {
+        // this warp's quarter of the row is on its way to global memory: hand it to the publisher warp (ring of 4 rows)
+        __syncwarp();
+        if (cx.lane == 0) {
+          if (kk >= 4 && seen + 3u < kk) {
+            uint32_t spins = 0;
+            while (*cx.pub_seen + 3u < kk) {
+              if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+            }
+          }
+          mbar_arrive(cx.pub_bar0 + 8u * (kk & 3u));
+        }
+      }
+    }
+    k += static_cast<uint32_t>(y1 - y0);
+  }
+  if (a.truth_hr != nullptr && a.loss_sum != nullptr) {
+    loss = warp_sum(loss);
+    if (cx.lane == 0) atomicAdd(a.loss_sum, static_cast<double>(loss));
+  }
+  return k;
+}
+
+template <int CIN, int NT, int NSTAGE, int WBUFS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Geom g, uint32_t* __restrict__ done, const int rot) {
+  using C_ = Cfg<CIN, NT, NSTAGE, WBUFS>;
+  constexpr int RING = C_::RING;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + WBUFS * C_::W_LAYER;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NSTAGE * C_::A_STAGE);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
+  auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + RING + b); };
+  auto wfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + b); };
+  auto wfree_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + WBUFS + b); };
+  auto pub_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C_::NBARS);
+  uint32_t* s_last = tmem_slot + 1;
+  volatile uint32_t* pub_seen = tmem_slot + 2;   // rows whose completion the publisher warp has observed
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full_bar(s), kProdThreads);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < RING; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), kEpiThreads / 2);
+    }
+    for (int b = 0; b < WBUFS; ++b) {
+      mbar_init(wfull_bar(b), 1);
+      mbar_init(wfree_bar(b), 1);
+    }
+    for (int s = 0; s < 4; ++s) mbar_init(pub_bar(s), kEpiWarps / 2);
+    tmem_slot[2] = 0u;
+    mbar_fence_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc<C_::TMEM_COLS>(smem_u32(tmem_slot));
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  const int G = static_cast<int>(gridDim.x);
+  // first job of this CTA in layer l: job X of layer l belongs to CTA (X + l*rot) mod G (spreads the partial last wave)
+  auto first_job = [&](int l) {
+    const int sh = static_cast<int>((static_cast<long long>(l) * rot) % G);
+    return (static_cast<int>(blockIdx.x) + G - sh) % G;
+  };
+  auto decode = [&](int job) {
+    Job j;
+    const int bk = job / g.nstrips;
+    j.u = job - bk * g.nstrips;
+    j.y0 = bk * g.rows_per_job;
+    j.y1 = min(g.H, j.y0 + g.rows_per_job);
+    return j;
+  };
+
+  if (warp == kPubWarp) {
+    // =============================== publisher: GPU-scope release of finished jobs ===============================
+    if (lane == 0 && nlayers > 1) {
+      uint32_t kk = 0;
+      for (int l = 0; l < nlayers; ++l) {
+        for (int job = first_job(l); job < g.total_jobs; job += G) {
+          const Job j = decode(job);
+          for (int yo = j.y0; yo < j.y1; ++yo, ++kk) {
+            mbar_wait(pub_bar(kk & 3u), (kk >> 2) & 1u);
+            *pub_seen = kk + 1u;
+          }
+          red_release_gpu_add(done + job, 1u);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp > kMmaWarp) {
+    // =============================== producers: dependency wait + input rows -> smem ===============================
+    const int ptid = threadIdx.x - (kEpiThreads + 32);
+    const int ddy = lane / 3 - 1, ddx = lane % 3 - 1;   // lanes 0..8 watch the 3x3 job neighbourhood
+    const size_t row_stride = static_cast<size_t>(C_::CH) * g.W * 8;   // elements between image rows
+    uint32_t fill = 0;
+    pdl_wait();
+    for (int l = 0; l < nlayers; ++l) {
+      const __nv_bfloat16* src_base = reinterpret_cast<const __nv_bfloat16*>(P.layer[l].src[0]);
+      for (int job = first_job(l); job < g.total_jobs; job += G) {
+        const Job j = decode(job);
+        // this thread's 16-byte pieces of a row buffer: piece idx = chunk * 130 + px  <->  shared-memory offset idx * 16
+        long long pc_off[C_::PIECES];
+#pragma unroll
+        for (int i = 0; i < C_::PIECES; ++i) {
+          const int idx = ptid + i * kProdThreads;
+          const int c = idx / kRowPx, px = idx - c * kRowPx;
+          const int p = j.u * kLanes - 1 + px;
+          long long off = -1;
+          if (idx < kRowPx * C_::CH && p >= 0) {
+            const int n = p / g.P, x = p - n * g.P;
+            if (n < g.N && x < g.W) off = ((static_cast<long long>(n) * g.H * C_::CH + c) * g.W + x) * 8;
+          }
+          pc_off[i] = off;
+        }
+        if (l > 0) {
+          if (lane < 9) {
+            const int bk = job / g.nstrips;
+            const int yy = bk + ddy, xx = j.u + ddx;
+            if (yy >= 0 && yy < g.nblocks && xx >= 0 && xx < g.nstrips)
+              wait_flag(done + yy * g.nstrips + xx, static_cast<uint32_t>(l));
+          }
+          __syncwarp();
+        }
+        const int ya = max(j.y0 - 1, 0), yb = min(j.y1 + 1, g.H);
+        for (int yi = ya; yi < yb; ++yi, ++fill) {
+          const int stage = fill % NSTAGE;
+          mbar_wait_relaxed(empty_bar(stage), ((fill / NSTAGE) & 1) ^ 1);
+          const __nv_bfloat16* src = src_base + static_cast<size_t>(yi) * row_stride;
+          const uint32_t dst0 = smem_u32(sA + stage * C_::A_STAGE) + ptid * 16;
+#pragma unroll
+          for (int i = 0; i < C_::PIECES; ++i) {
+            if (ptid + i * kProdThreads < kRowPx * C_::CH) {
+              const bool inb = pc_off[i] >= 0;
+              cp_async16(dst0 + i * (kProdThreads * 16), inb ? (src + pc_off[i]) : src_base, inb ? 16u : 0u);
+            }
+          }
+          cp_async_mbar_arrive_noinc(full_bar(stage));
+        }
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp == kMmaWarp) {
+    // =============================== MMA issuer (one elected lane) ================================
+    if (elect_one()) {
+      auto load_weights = [&](int l) {
+        const int b = l % WBUFS;
+        mbar_arrive_expect_tx(wfull_bar(b), C_::W_LAYER);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(P.layer[l].weights);
+        for (int t = 0; t < 3 * C_::CH; ++t)
+          tma_bulk_g2s(smem_u32(sW + b * C_::W_LAYER + t * C_::W_PLANE), wsrc + static_cast<size_t>(t) * C_::W_PLANE,
+                       C_::W_PLANE, wfull_bar(b));
+      };
+      load_weights(0);   // packed weights are never written while a launch chain is in flight: no pdl_wait needed
+      uint32_t fill = 0, k = 0;
+      uint32_t free_pending = 0, free_phase = 0;   // bit b: MMAs reading weight buffer b outstanding / wfree parity
+      for (int l = 0; l < nlayers; ++l) {
+        const int wb = l % WBUFS;
+        if (l + 1 < nlayers) {
+          const int nb = (l + 1) % WBUFS;
+          if (free_pending & (1u << nb)) {
+            mbar_wait(wfree_bar(nb), (free_phase >> nb) & 1u);
+            free_phase ^= 1u << nb;
+            free_pending &= ~(1u << nb);
+          }
+          load_weights(l + 1);
+        }
+        mbar_wait(wfull_bar(wb), (l / WBUFS) & 1);
+        const uint32_t sW_addr = smem_u32(sW + wb * C_::W_LAYER);
+        bool any = false;
+        for (int job = first_job(l); job < g.total_jobs; job += G) {
+          const Job j = decode(job);
+          const int ya = max(j.y0 - 1, 0), yb = min(j.y1 + 1, g.H);
+          for (int yi = ya; yi < yb; ++yi, ++fill) {
+            // targets t = 0,1,2: output row yi+1-t through vertical tap ky = t (weight rows [t*NT, (t+1)*NT));
+            // the valid ones form an interval [ta, tb]
+            int ta = 3, tb = -1;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+              const int r = yi + 1 - t;
+              if (r >= j.y0 && r < j.y1) { ta = min(ta, t); tb = t; }
+            }
+            // accumulator-ring counter of target t's output row; its block sits at column (RING-1 - kk % RING) * NT,
+            // so the blocks of targets t, t+1 are adjacent (ascending) unless kk_t % RING == 0 (the ring wraps there)
+            const uint32_t kk0 = k + static_cast<uint32_t>(yi + 1 - j.y0);      // target 0 (may be "virtual" when invalid)
+            auto col_of = [&](int t) { return (RING - 1 - ((kk0 - static_cast<uint32_t>(t)) % RING)) * NT; };
+            // Runs = maximal groups of valid targets issued as ONE MMA (adjacent blocks, N = NT * targets).  `rr`: every
+            // MMA but the row's first; `fr`: the first (kx = 0, k-step 0), which must additionally separate blocks it
+            // OVERWRITES (first contribution to that output row: target 0 always, target 1 on the image's top row)
+            // from blocks it accumulates into -- the flag is per instruction.
+            uint32_t rr_d[2], rr_b[2], rr_i[2], fr_d[3], fr_b[3], fr_i[3], fr_acc[3];
+            int nr = 0, nf = 0;
+            if (ta <= tb) {
+              int ts = ta;
+              while (ts <= tb) {
+                int te = ts;
+                while (te < tb && ((kk0 - static_cast<uint32_t>(te)) % RING) != 0) ++te;
+                rr_d[nr] = tmem_base + col_of(ts);
+                rr_b[nr] = static_cast<uint32_t>(ts * NT);          // weight row offset (16 B per row)
+                rr_i[nr] = idesc_n((te - ts + 1) * NT);
+                ++nr;
+                // the same run for the first MMA, cut after target 0 when the rest accumulates
+                int fs = ts;
+                if (yi > 0 && ts == 0 && te > 0) {
+                  fr_d[nf] = tmem_base + col_of(0); fr_b[nf] = 0; fr_i[nf] = idesc_n(NT); fr_acc[nf] = 0u; ++nf;
+                  fs = 1;
+                }
+                fr_d[nf] = tmem_base + col_of(fs);
+                fr_b[nf] = static_cast<uint32_t>(fs * NT);
+                fr_i[nf] = idesc_n((te - fs + 1) * NT);
+                fr_acc[nf] = (yi == 0 || fs == 0) ? 0u : 1u;
+                ++nf;
+                ts = te + 1;
+              }
+              // blocks overwritten by this row must have been drained by the epilogue (their previous output row)
+              if (ta == 0) {
+                mbar_wait(tempty_bar(kk0 % RING), ((kk0 / RING) & 1u) ^ 1u);
+              }
+              if (yi == 0 && tb >= 1) {
+                const uint32_t kk1 = kk0 - 1u;
+                mbar_wait(tempty_bar(kk1 % RING), ((kk1 / RING) & 1u) ^ 1u);
+              }
+            }
+            const int stage = fill % NSTAGE;
+            mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
+            fence_proxy_async_smem();
+            tc_fence_after_sync();
+            if (nr > 0) {
+              const uint64_t adesc0 = umma_smem_desc(smem_u32(sA + stage * C_::A_STAGE), C_::A_PLANE, 128);
+              const uint64_t bdesc0 = umma_smem_desc(sW_addr, C_::W_PLANE, 128);
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                for (int ks = 0; ks < C_::KSTEPS; ++ks) {
+                  // descriptor start addresses move in 16-byte units: horizontal tap = one pixel, k-step = two chunk planes
+                  const uint64_t adesc = adesc0 + static_cast<uint64_t>((kx * 16 + 2 * ks * C_::A_PLANE) >> 4);
+                  const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((kx * C_::W_KX + 2 * ks * C_::W_PLANE) >> 4);
+                  if (kx == 0 && ks == 0) {
+                    for (int i = 0; i < nf; ++i) umma_bf16(fr_d[i], adesc, bdesc + fr_b[i], fr_i[i], fr_acc[i]);
+                  } else {
+                    umma_bf16(rr_d[0], adesc, bdesc + rr_b[0], rr_i[0], 1u);
+                    if (nr > 1) umma_bf16(rr_d[1], adesc, bdesc + rr_b[1], rr_i[1], 1u);
+                  }
+                }
+              }
+            }
+            umma_commit(empty_bar(stage));   // row buffer reusable once these MMAs retire
+            // output rows this input row completes: yi-1 always, yi too on the image's bottom row
+            if (yi - 1 >= j.y0 && yi - 1 < j.y1) umma_commit(tfull_bar((k + static_cast<uint32_t>(yi - 1 - j.y0)) % RING));
+            if (yi == g.H - 1 && yi >= j.y0 && yi < j.y1) umma_commit(tfull_bar((k + static_cast<uint32_t>(yi - j.y0)) % RING));
+            any = true;
+          }
+          k += static_cast<uint32_t>(j.y1 - j.y0);
+        }
+        if (any) {
+          umma_commit(wfree_bar(wb));
+          free_pending |= 1u << wb;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue: TMEM -> registers -> global ========================
+    EpiCtx cx;
+    cx.eg = warp >> 2;
+    const int q = warp & 3;
+    cx.m = q * 32 + lane;
+    cx.lane = lane;
+    cx.g = g;
+    cx.done = done;
+    cx.pub_seen = pub_seen;
+    cx.tfull0 = tfull_bar(0);
+    cx.tempty0 = tempty_bar(0);
+    cx.pub_bar0 = pub_bar(0);
+    cx.tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    cx.G = G;
+    cx.nlayers = nlayers;
+    cx.chunk_stride = static_cast<size_t>(g.W) * 8;
+    cx.row_stride = static_cast<size_t>(NT / 8) * g.W * 8;
+
+    pdl_wait();
+    uint32_t k = 0;   // CTA-local output-row counter; this group handles the rows with k % 2 == eg
+    for (int l = 0; l < nlayers; ++l) {
+      const lv_conv_args& a = P.layer[l];
+      const bool has_ops = (a.mask != nullptr) || (a.res1 != nullptr) || (a.res2 != nullptr);
+      int kind = kKindGeneric;
+      if (a.cout == NT && a.res_scale == 1.0f) {
+        if (a.epilogue == LV_EPI_NHWC) {
+          const int code = (a.relu ? 1 : 0) | (a.mask ? 2 : 0) | (a.res1 ? 4 : 0) | (a.res2 ? 8 : 0);
+          if (code == 0 || code == 1 || code == 2 || code == 4 || code == 12) kind = code;
+        } else if (NT == 48 && a.epilogue == LV_EPI_PS4_NCHW && !a.relu && !has_ops) {
+          kind = kKindPs4;
+        }
+      }
+      const int first = first_job(l);
+      switch (kind) {
+        case 0: k = run_layer<0, NT, RING>(cx, a, l, first, k); break;
+        case 1: k = run_layer<1, NT, RING>(cx, a, l, first, k); break;
+        case 2: k = run_layer<2, NT, RING>(cx, a, l, first, k); break;
+        case 4: k = run_layer<4, NT, RING>(cx, a, l, first, k); break;
+        case 12: k = run_layer<12, NT, RING>(cx, a, l, first, k); break;
+        case kKindPs4:
+          if constexpr (NT == 48) { k = run_layer<kKindPs4, NT, RING>(cx, a, l, first, k); break; }
+        default: k = run_layer<kKindGeneric, NT, RING>(cx, a, l, first, k); break;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after_sync();
+    tmem_dealloc<C_::TMEM_COLS>(tmem_base);
+  }
+  if (nlayers > 1) {
+    // self-cleaning workspace: done[total_jobs] is the exit counter; the last CTA out resets everything
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t prev = atomicAdd(done + g.total_jobs, 1u);
+      *s_last = (prev == static_cast<uint32_t>(G) - 1u) ? 1u : 0u;
+      __threadfence();
+    }
+    __syncthreads();
+    if (*s_last != 0u) {
+      for (int i = threadIdx.x; i <= g.total_jobs; i += kThreads) done[i] = 0u;
+    }
+  }
+}
+
+// rows per job: minimise (rounds of jobs per CTA) x (rows + ~1.7 halo-row equivalents); short jobs keep every SM busy on
+// small problems, long jobs amortise the two halo rows on large ones
+static Geom make_geom(int n, int h, int w, int ctas) {
+  Geom g;
+  g.N = n; g.H = h; g.W = w; g.P = w + 1;
+  const long long line = static_cast<long long>(n) * g.P - 1;
+  g.nstrips = static_cast<int>((line + kLanes - 1) / kLanes);
+  if (g.nstrips < 1) g.nstrips = 1;
+  double best = 1e300;
+  int best_r = 1;
+  for (int r = 1; r <= h; ++r) {
+    const long long jobs = static_cast<long long>(g.nstrips) * ((h + r - 1) / r);
+    const long long rounds = (jobs + ctas - 1) / ctas;
+    const double cost = static_cast<double>(rounds) * (r + 1.7);
+    if (cost < best - 1e-9) { best = cost; best_r = r; }
+  }
+  g.rows_per_job = best_r;
+  g.nblocks = (h + best_r - 1) / best_r;
+  g.total_jobs = g.nstrips * g.nblocks;
+  return g;
+}
+
+}  // namespace row
+
+long long conv3x3_row_workspace_bytes(int n, int h, int w) {
+  const long long line = static_cast<long long>(n) * (w + 1) - 1;
+  long long strips = (line + row::kLanes - 1) / row::kLanes;
+  if (strips < 1) strips = 1;
+  return (strips * (h > 0 ? h : 1) + 1) * 4;   // one flag per job at worst (1 row per job) + the exit counter
+}
+
+// checks the persistent grid can be co-resident (the data-flow waits need every CTA running) and opts into the
+// dynamic shared memory, once per device
+template <typename K>
+static int prepare_kernel(K kern, size_t smem, int threads, int grid, bool needs_coresidency) {
+  static size_t configured[64] = {0};
+  int dev = 0;
+  LV_CUDA_OK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (configured[dev] < smem) {
+    LV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    LV_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+    if (per_sm < 1) {
+      set_error("conv row kernel: a CTA (%zu B shared memory, %d threads) does not fit on an SM of device %d", smem, threads, dev);
+      return LV_ERR_UNSUPPORTED;
+    }
+    configured[dev] = smem;
+  }
+  if (needs_coresidency && grid > sm_count()) {
+    set_error("conv row chain: grid %d exceeds the %d SMs that can hold one resident CTA each", grid, sm_count());
+    return LV_ERR_UNSUPPORTED;
+  }
+  return LV_OK;
+}
+
+template <int CIN, int NT, int NSTAGE, int WBUFS>
+static int launch_row(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
+                      cudaStream_t stream) {
+  using C_ = row::Cfg<CIN, NT, NSTAGE, WBUFS>;
+  const lv_conv_args& a0 = layers[0];
+  int ctas = max_ctas > 0 ? max_ctas : sm_count();
+  if (ctas > sm_count()) ctas = sm_count();
+  row::Geom g = row::make_geom(a0.n, a0.h, a0.w, ctas);
+  if (g.total_jobs < ctas) ctas = g.total_jobs;
+  if (count > 1) {
+    LV_CHECK_ARG(sync_ws != nullptr && sync_ws_bytes >= (static_cast<long long>(g.total_jobs) + 1) * 4,
+                 "conv row chain: sync workspace too small (%lld < %lld bytes)", sync_ws_bytes,
+                 (static_cast<long long>(g.total_jobs) + 1) * 4);
+  }
+  auto kern = row::conv3x3_row_kernel<CIN, NT, NSTAGE, WBUFS>;
+  int rc = prepare_kernel(kern, C_::smem_bytes(), row::kThreads, ctas, count > 1);
+  if (rc != LV_OK) return rc;
+  static thread_local row::Params params;   // staging only; the launch copies it by value
+  for (int i = 0; i < count; ++i) params.layer[i] = layers[i];
+  const int rot = g.total_jobs % ctas;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(row::kThreads);
+  cfg.dynamicSmemBytes = C_::smem_bytes();
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, params, count, g, static_cast<uint32_t*>(sync_ws), rot));
+  count_launch();
+  return LV_OK;
+}
+
+bool conv3x3_row_supported(const lv_conv_args& a) {
+  return a.dtype == LV_BF16 && a.wlayout == LV_W_KY_STACKED && a.num_src == 1 && a.cin == a.cout && (a.cin == 48 || a.cin == 64) &&
+         (a.epilogue == LV_EPI_NHWC || (a.epilogue == LV_EPI_PS4_NCHW && a.cout == 48));
+}
+
+// layers[0..count): single-source bf16 C -> C convs (C = 48 or 64, the same for all) with ky-stacked weights on one common
+// (n, h, w); count == 1 needs no workspace.
+int conv3x3_row_chain(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
+                      cudaStream_t stream) {
+  LV_CHECK_ARG(count >= 1 && count <= row::kMaxLayers, "conv row chain: 1..%d layers per call (got %d)", row::kMaxLayers, count);
+  const lv_conv_args& a0 = layers[0];
+  for (int i = 0; i < count; ++i) {
+    const lv_conv_args& a = layers[i];
+    LV_CHECK_ARG(conv3x3_row_supported(a) && a.cin == a0.cin,
+                 "conv row kernel: layer %d is not a single-source bf16 %d->%d conv with ky-stacked weights", i, a0.cin, a0.cin);
+    LV_CHECK_ARG(a.n == a0.n && a.h == a0.h && a.w == a0.w, "conv row chain: layer %d has a different geometry", i);
+  }
+  if (static_cast<long long>(a0.n) * a0.h * a0.w == 0) return LV_OK;
+  LV_CHECK_ARG(static_cast<long long>(a0.n) * (a0.w + 1) < (1ll << 30), "conv row kernel: batch x width too large");
+  if (a0.cin == 48) return launch_row<48, 48, 8, 3>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
+  return launch_row<64, 64, 4, 2>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
+}
+
+}  // namespace lv

@@ -377,10 +377,11 @@ static int launch_tc(const lv_conv_args& a, const ConvGeom& g, int max_ctas, cud
   using Cfg = TcCfg<CIN, NT, NSTAGE>;
   const size_t smem = Cfg::smem_bytes(a.num_src, g.cout_pad);
   auto kern = conv3x3_tc_kernel<CIN, NT, NSTAGE, EPI>;
-  static size_t configured = 0;
-  if (smem > configured) {
+  static size_t configured[64] = {0};   // per device
+  const int dev = current_device_slot();
+  if (smem > configured[dev]) {
     LV_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
+    configured[dev] = smem;
   }
   long long ctas = max_ctas > 0 ? max_ctas : sm_count();
   if (ctas > g.total_tiles) ctas = g.total_tiles;

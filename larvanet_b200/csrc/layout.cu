@@ -324,9 +324,68 @@ struct FusedBatch {
   int nconv, nrows, nbricks, brick_blocks;
 };
 
-__device__ __forceinline__ float adamw_one(float* p, const float* g, float* m, float* v, long long i, float lr, float b1,
-                                           float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
-  const float grad = g[i] * gscale;
+// ---- data-parallel variant: the gradient of element i is the SUM over all ranks' gradient arenas, read straight out of
+// the peers' HBM over NVLink (symmetric / peer-mapped memory), in rank order on every rank -- so every rank computes the
+// bit-identical sum and the replicas' weights never drift apart.  One kernel = device-side barrier ("every rank's
+// gradients are complete") + all-reduce + AdamW + operand re-pack + device-side barrier ("every rank is done reading").
+constexpr int kDpMaxRanks = 16, kDpFlagWords = 2 * kDpMaxRanks;
+struct DpCtx {
+  const float* grad[kDpMaxRanks];     // gradient arena of rank r (peer-mapped address on this device)
+  uint32_t* flags[kDpMaxRanks];       // flag block of rank r: [start barrier: slot per writer rank][end barrier: same]
+  const double* loss[kDpMaxRanks];    // local loss accumulator of rank r
+  double* loss_out;                   // this rank: sum over ranks
+  uint32_t* ctl;                      // this rank, device-local control words: [0] epoch, [1] go, [2] blocks arrived
+  int world, rank;
+};
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// peer memory is not cached in the local L2; bypass L1 too so that a line read in an earlier step is never reused
+__device__ __forceinline__ float ld_peer_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until_sys(const uint32_t* p, uint32_t need) {
+  uint32_t spins = 0;
+  while (ld_acquire_sys(p) < need) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) asm volatile("trap;");   // ~1-2 s: a peer died; fail loudly instead of hanging the GPU
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ float grad_at(const float* g, const DpCtx& dp, long long i) {
+  if constexpr (NP == 0) {
+    return g[i];
+  } else {
+    float part[NP];
+#pragma unroll
+    for (int r = 0; r < NP; ++r) part[r] = ld_peer_f32(dp.grad[r] + i);   // all loads in flight before the first add
+    float s = part[0];
+#pragma unroll
+    for (int r = 1; r < NP; ++r) s += part[r];
+    return s;
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ float adamw_one(float* p, const float* g, const DpCtx& dp, float* m, float* v, long long i, float lr,
+                                           float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  const float grad = grad_at<NP>(g, dp, i) * gscale;
   float pv = p[i] * (1.f - lr * wd);
   const float mv = m[i] + (grad - m[i]) * (1.f - b1);            // lerp_, as torch does
   const float vv = v[i] * b2 + (1.f - b2) * grad * grad;
@@ -336,17 +395,80 @@ __device__ __forceinline__ float adamw_one(float* p, const float* g, float* m, f
   return pv;
 }
 
+// entry barrier of the data-parallel kernel; returns this launch's epoch
+template <int NP>
+__device__ __forceinline__ uint32_t dp_enter(const DpCtx& dp) {
+  __shared__ uint32_t s_epoch;
+  const int t = threadIdx.x;
+  if (t == 0) s_epoch = ld_acquire_gpu_u32(dp.ctl) + 1u;   // committed by the last block to leave
+  __syncthreads();
+  const uint32_t e = s_epoch;
+  if (blockIdx.x == 0) {
+    // tell every rank "my gradients (written by earlier kernels of my stream) are complete", wait for everybody's
+    if (t < NP) {
+      st_release_sys(dp.flags[t] + dp.rank, e);
+      spin_until_sys(dp.flags[dp.rank] + t, e);
+    }
+    __syncthreads();
+    if (t == 0) {
+      double s = 0.0;
+      for (int r = 0; r < NP; ++r) s += *reinterpret_cast<const volatile double*>(dp.loss[r]);
+      *dp.loss_out = s;
+      st_release_gpu(dp.ctl + 1, e);   // lets the other blocks of this grid go
+    }
+  } else {
+    if (t == 0) {
+      uint32_t spins = 0;
+      while (ld_acquire_gpu_u32(dp.ctl + 1) < e) {
+        __nanosleep(64);
+        if (++spins > (1u << 24)) asm volatile("trap;");
+      }
+    }
+  }
+  __syncthreads();
+  return e;
+}
+
+// exit barrier: the last block of the grid tells every rank "I am done reading your arena" and waits until every rank
+// is done reading this one -- only then may the kernels that follow in this stream overwrite the gradients / loss
+template <int NP>
+__device__ __forceinline__ void dp_leave(const DpCtx& dp, uint32_t e) {
+  __shared__ uint32_t s_last;
+  const int t = threadIdx.x;
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    const uint32_t prev = atomicAdd(dp.ctl + 2, 1u);
+    s_last = (prev == gridDim.x - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last == 0u) return;
+  if (t < NP) {
+    st_release_sys(dp.flags[t] + kDpMaxRanks + dp.rank, e);
+    spin_until_sys(dp.flags[dp.rank] + kDpMaxRanks + t, e);
+  }
+  __syncthreads();
+  if (t == 0) {
+    dp.ctl[2] = 0u;
+    st_release_gpu(dp.ctl, e);
+  }
+}
+
+template <int NP>
 __global__ void __launch_bounds__(192)
 adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                  const __grid_constant__ FusedBatch fb, float lr, float b1, float b2, float eps, float wd, float bc1,
-                  float bc2_sqrt, float gscale) {
+                  const __grid_constant__ FusedBatch fb, const __grid_constant__ DpCtx dp, float lr, float b1, float b2,
+                  float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
   __shared__ float sm[8][72];   // [oo][ii*9 + tap]
   const int t = threadIdx.x;
+  uint32_t epoch = 0;
+  if constexpr (NP > 0) epoch = dp_enter<NP>(dp);
   if (static_cast<int>(blockIdx.x) >= fb.brick_blocks) {   // biases, head conv, anything without a packed operand
     const int row = (static_cast<int>(blockIdx.x) - fb.brick_blocks) * kFusedRowsPerBlock + t / kFusedRow;
     const int i = t % kFusedRow;
     if (row < fb.nrows && i < fb.row_cnt[row])
-      adamw_one(p, g, m, v, fb.row_off[row] + i, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      adamw_one<NP>(p, g, dp, m, v, fb.row_off[row] + i, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+    if constexpr (NP > 0) dp_leave<NP>(dp, epoch);
     return;
   }
   for (int brick = blockIdx.x; brick < fb.nbricks; brick += fb.brick_blocks) {
@@ -362,7 +484,7 @@ adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
       const int e = t + 192 * r;                 // 0..575
       const int oo = e / 72, rem = e - oo * 72;  // rem = ii*9 + tap: 72 contiguous floats of output channel 8*ob+oo
       const long long idx = cv.w_off + (static_cast<long long>(8 * ob + oo) * cv.I + 8 * ib) * 9 + rem;
-      sm[oo][rem] = adamw_one(p, g, m, v, idx, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      sm[oo][rem] = adamw_one<NP>(p, g, dp, m, v, idx, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
     }
     __syncthreads();
     const int s = ib / 6, chunk = ib - 6 * s;    // source slice and 8-channel chunk of the brick's input channels
@@ -388,15 +510,11 @@ adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
       *reinterpret_cast<uint4*>(cv.bwd[s] + off) = q;
     }
   }
+  if constexpr (NP > 0) dp_leave<NP>(dp, epoch);
 }
 
-int adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs,
-                    int nconv, cudaStream_t stream) {
-  if (numel == 0) return LV_OK;
-  LV_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+static int build_fused_batch(FusedBatch& fb, long long numel, const lv_fused_conv* convs, int nconv) {
   LV_CHECK_ARG(convs != nullptr && nconv >= 1 && nconv <= kFusedMaxConvs, "adamw+pack: 1..%d convs per call", kFusedMaxConvs);
-  static thread_local FusedBatch fb;
   // convs must be sorted by offset and disjoint; everything between them becomes a plain range
   long long pos = 0;
   int nr = 0, bricks = 0;
@@ -430,12 +548,70 @@ int adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_
     ++nr;
   }
   fb.nconv = nconv; fb.nrows = nr; fb.nbricks = bricks;
+  fb.brick_blocks = bricks < 148 * 8 ? bricks : 148 * 8;
+  return LV_OK;
+}
+
+int adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs,
+                    int nconv, cudaStream_t stream) {
+  if (numel == 0) return LV_OK;
+  LV_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+  static thread_local FusedBatch fb;
+  static thread_local DpCtx none;   // unused by the single-process instantiation
+  int rc = build_fused_batch(fb, numel, convs, nconv);
+  if (rc != LV_OK) return rc;
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
-  fb.brick_blocks = bricks < 148 * 8 ? bricks : 148 * 8;
-  const int tail_blocks = (nr + kFusedRowsPerBlock - 1) / kFusedRowsPerBlock;
-  adamw_pack_kernel<<<fb.brick_blocks + tail_blocks, 192, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, fb, lr, beta1, beta2, eps, weight_decay,
-                                                  static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), grad_scale);
+  const int tail_blocks = (fb.nrows + kFusedRowsPerBlock - 1) / kFusedRowsPerBlock;
+  adamw_pack_kernel<0><<<fb.brick_blocks + tail_blocks, 192, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, fb, none, lr, beta1, beta2,
+                                                                       eps, weight_decay, static_cast<float>(bc1),
+                                                                       static_cast<float>(sqrt(bc2)), grad_scale);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+// Data-parallel optimizer step: gradient all-reduce over peer memory + AdamW + operand re-pack in ONE kernel (see DpCtx).
+int dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs, int nconv,
+                       const void* const* peer_grads, void* const* peer_flags, const void* const* peer_loss, double* loss_out,
+                       uint32_t* ctl, int world, int rank, cudaStream_t stream) {
+  if (numel == 0) return LV_OK;
+  LV_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
+  LV_CHECK_ARG(world == 2 || world == 4 || world == 8, "dp adamw: world size must be 2, 4 or 8 (got %d)", world);
+  LV_CHECK_ARG(rank >= 0 && rank < world, "dp adamw: rank %d outside 0..%d", rank, world - 1);
+  LV_CHECK_ARG(peer_grads && peer_flags && peer_loss && loss_out && ctl, "dp adamw: null pointer");
+  static thread_local FusedBatch fb;
+  static thread_local DpCtx dp;
+  int rc = build_fused_batch(fb, numel, convs, nconv);
+  if (rc != LV_OK) return rc;
+  for (int r = 0; r < world; ++r) {
+    LV_CHECK_ARG(peer_grads[r] && peer_flags[r] && peer_loss[r], "dp adamw: null pointer for rank %d", r);
+    dp.grad[r] = static_cast<const float*>(peer_grads[r]);
+    dp.flags[r] = static_cast<uint32_t*>(peer_flags[r]);
+    dp.loss[r] = static_cast<const double*>(peer_loss[r]);
+  }
+  dp.loss_out = loss_out;
+  dp.ctl = ctl;
+  dp.world = world;
+  dp.rank = rank;
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  const int tail_blocks = (fb.nrows + kFusedRowsPerBlock - 1) / kFusedRowsPerBlock;
+  const int grid = fb.brick_blocks + tail_blocks;
+  const float* g = dp.grad[rank];
+#define LV_DP_CASE(NPV)                                                                                                   \
+  case NPV:                                                                                                               \
+    adamw_pack_kernel<NPV><<<grid, 192, 0, stream>>>(param, g, exp_avg, exp_avg_sq, fb, dp, lr, beta1, beta2, eps,         \
+                                                     weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), \
+                                                     grad_scale);                                                         \
+    break;
+  switch (world) {
+    LV_DP_CASE(2)
+    LV_DP_CASE(4)
+    LV_DP_CASE(8)
+  }
+#undef LV_DP_CASE
   LV_LAUNCH_OK();
   return LV_OK;
 }

@@ -14,6 +14,14 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
 
+// Per-DEVICE one-time configuration (cudaFuncSetAttribute applies to the current device only): returns the slot of the
+// current device in a kernel-specific `state[64]` table.
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
+
 #define LV_CHECK_ARG(cond, ...)                   \
   do {                                            \
     if (!(cond)) {                                \

@@ -437,11 +437,12 @@ int wgrad_simt(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, 
     cout = items_host[k].cout > cout ? items_host[k].cout : cout;
   }
   const size_t smem = (static_cast<size_t>(kSWHaloPix) * (cin + 1) + 128 * (cout + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};   // per device
+  const int dev = current_device_slot();
+  if (!configured[dev]) {
     LV_CUDA_OK(cudaFuncSetAttribute(wgrad_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     LV_CUDA_OK(cudaFuncSetAttribute(wgrad_simt_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
+    configured[dev] = true;
   }
   if (items_host[0].dtype == LV_F32)
     wgrad_simt_kernel<float><<<dim3(splits, count), 256, smem, stream>>>(items_dev, splits);
@@ -517,10 +518,11 @@ int wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int c
     return wgrad_simt(items_host, items_dev, count, splits, stream);
   }
   LV_CHECK_ARG(workspace != nullptr, "wgrad: workspace required");
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {false};   // per device
+  const int dev = current_device_slot();
+  if (!configured[dev]) {
     LV_CUDA_OK(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
-    configured = true;
+    configured[dev] = true;
   }
   static thread_local WMaps maps;   // staging only; the launches copy them by value
   static thread_local WSched sc;

@@ -61,39 +61,94 @@ class SymmetricGradExchange:
     Construction is collective.  Every rank reports success or failure and the group only switches over if ALL ranks
     succeeded; otherwise everybody keeps the NCCL all-reduce (`allreduce_gradients`)."""
 
+    TAIL = 64   # floats behind the gradient arena: [0:2] this rank's loss (one double), [16:48] device-barrier flags
+
     def __init__(self, numel, device, group=None):
+        """Local half of the construction (no collective): allocate this rank's symmetric buffer."""
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.group_name = self.group.group_name
-        world = dist.get_world_size(self.group)
-        pad = 4 * 32 * world                       # 16-byte vectors x 32 lanes x ranks: keeps every rank's share aligned
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        pad = 4 * 32 * self.world                  # 16-byte vectors x 32 lanes x ranks: keeps every rank's share aligned
         self.numel = (int(numel) + pad - 1) // pad * pad
-        self.buffer = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
-        self.buffer.zero_()
-        self.handle = symm_mem.rendezvous(self.buffer, self.group_name)
+        self.storage = symm_mem.empty(self.numel + self.TAIL, dtype=torch.float32, device=device)
+        self.storage.zero_()
+        self.buffer = self.storage[:self.numel]    # the gradient arena the engine writes into
+        self.loss_view = self.storage[self.numel:self.numel + 2].view(torch.float64)   # this rank's loss accumulator
+        self.handle = None
+        self.peers = None
+
+    def rendezvous(self):
+        """Collective half: exchange the peer mappings.  Only entered once EVERY rank has allocated successfully."""
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        self.handle = symm_mem.rendezvous(self.storage, self.group_name)
+        # raw peer addresses for the fused all-reduce + AdamW kernel (lv_dp_adamw_pack_step); None if the handle does
+        # not expose them (then the engine keeps the two-shot all-reduce + separate optimizer launch)
+        try:
+            bases = [int(p) + int(getattr(self.handle, 'offset', 0)) for p in self.handle.buffer_ptrs]
+            if len(bases) == self.world and bases[self.rank] == self.storage.data_ptr():
+                self.peers = PeerArena(self, bases, C)
+        except Exception:  # noqa: BLE001
+            self.peers = None
 
     def allreduce_(self):
         torch.ops.symm_mem.two_shot_all_reduce_(self.buffer, 'sum', self.group_name)
 
     @staticmethod
+    def _agree(ok, device, group):
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return int(flag.item()) == 1
+
+    @staticmethod
     def try_create(numel, device, group=None):
-        """Collective: returns an exchange on every rank or None on every rank."""
-        ok, ex = 1, None
+        """Collective: returns an exchange on every rank or None on every rank.  Two agreement rounds (plain NCCL MIN
+        all-reduces) bracket the symmetric-memory collectives, so a rank whose LOCAL allocation fails (OOM, unsupported)
+        never leaves its peers blocked inside the rendezvous: nobody enters it unless everybody allocated."""
+        import sys
+        ex, why = None, None
         if os.environ.get('LARVANET_B200_SYMM_ALLREDUCE', '1') == '0':
-            ok = 0
+            why = 'disabled by LARVANET_B200_SYMM_ALLREDUCE=0'
         else:
             try:
                 ex = SymmetricGradExchange(numel, device, group)
-                ex.allreduce_()                   # one warm-up exchange (zeros) also proves the kernel runs here
-                torch.cuda.synchronize(device)
             except Exception as e:  # noqa: BLE001 -- any failure means "use NCCL", agreed on collectively below
-                ok, ex = 0, None
-                import sys
-                print(f'[larvanet_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL',
-                      file=sys.stderr)
-        flag = torch.tensor([ok], dtype=torch.int32, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        return ex if int(flag.item()) == 1 else None
+                ex, why = None, f'{type(e).__name__}: {e}'
+        if not SymmetricGradExchange._agree(ex is not None, device, group):
+            if why is not None and not why.startswith('disabled'):
+                print(f'[larvanet_b200] symmetric-memory allocation failed here ({why}); every rank uses NCCL', file=sys.stderr)
+            return None
+        ok = True
+        try:
+            ex.rendezvous()
+            ex.allreduce_()                       # one warm-up exchange (zeros) also proves the kernel runs here
+            torch.cuda.synchronize(device)
+        except Exception as e:  # noqa: BLE001
+            ok = False
+            print(f'[larvanet_b200] symmetric-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL', file=sys.stderr)
+        if not SymmetricGradExchange._agree(ok, device, group):
+            return None
+        # the fused exchange+optimizer kernel is used only if EVERY rank has the peer addresses
+        if not SymmetricGradExchange._agree(ex.peers is not None and ex.peers.supported, device, group):
+            ex.peers = None
+        return ex
+
+
+class PeerArena:
+    """Raw peer-mapped addresses of every rank's gradient arena / loss slot / flag block (ctypes arrays, index = rank)
+    plus this rank's device-local control words: the arguments of `ops.dp_adamw_pack_step`."""
+
+    def __init__(self, ex, bases, C):
+        self.world, self.rank = ex.world, ex.rank
+        n = ex.numel
+        self.grad_ptrs = (C.c_void_p * self.world)(*bases)
+        self.loss_ptrs = (C.c_void_p * self.world)(*[b + n * 4 for b in bases])
+        self.flag_ptrs = (C.c_void_p * self.world)(*[b + (n + 16) * 4 for b in bases])
+        self.loss_out = torch.zeros(1, dtype=torch.float64, device=ex.storage.device)   # sum over ranks, written by the kernel
+        self.ctl = torch.zeros(4, dtype=torch.int32, device=ex.storage.device)
+        self.supported = self.world in (2, 4, 8)
 
 
 def frames_for_rank(num_frames, rank, world):

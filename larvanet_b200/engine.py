@@ -127,6 +127,52 @@ def _capture_graph(run):
     return None, 0
 
 
+class _ShapeCache:
+    """Per-input-shape buffer sets + captured CUDA graphs, bounded: least-recently-used shapes are dropped (their buffers
+    and graph pool are freed) once more than `capacity` are alive, and a shape is only captured into a graph the second
+    time it is seen -- validate.py / get_sr.py walk over images of ~100 different sizes, each seen once per pass, and
+    must neither accumulate hundreds of MB per size nor pay a warm-up + capture pass for a one-off shape."""
+
+    def __init__(self, capacity):
+        import collections
+        self.capacity = max(1, int(capacity))
+        self.entries = collections.OrderedDict()   # key -> dict(bufs, graph, launches, hits)
+
+    def get(self, key, build):
+        ent = self.entries.get(key)
+        if ent is None:
+            while len(self.entries) >= self.capacity:
+                _, old = self.entries.popitem(last=False)
+                old['graph'] = None
+                old['bufs'] = None
+            ent = dict(bufs=build(), graph=None, launches=0, hits=0)
+            self.entries[key] = ent
+        else:
+            self.entries.move_to_end(key)
+        ent['hits'] += 1
+        return ent
+
+    def clear(self):
+        self.entries.clear()
+
+    def __len__(self):
+        return len(self.entries)
+
+
+def _run_cached(engine, ent, run):
+    """Run `run()` for a cached shape: eagerly the first time, through a CUDA graph (captured on the second use) after."""
+    if engine.use_graphs and not engine.simt and ent['hits'] >= 2:
+        if ent['graph'] is None:
+            g, nl = _capture_graph(run)
+            ent['graph'] = g if g is not None else False
+            ent['launches'] = nl
+        if ent['graph']:
+            ent['graph'].replay()
+            engine.replayed_launches += ent['launches']
+            return
+    run()
+
+
 class LarvaEngine:
     def __init__(self, module, blocks, v2=False, act_dtype=torch.bfloat16, device=None, use_graphs=None):
         self.module = module
@@ -149,19 +195,24 @@ class LarvaEngine:
         self._alloc_packed()
         self._packed_version = None
         self._packed_bwd = False
-        self._infer = {}   # shape -> (bufs, graph)
-        self._train = {}
+        cap = int(os.environ.get('LARVANET_B200_SHAPE_CACHE', '4'))
+        self._infer = _ShapeCache(cap)   # (n, h, w, exit_leg) -> buffers + graph, LRU-bounded
+        self._train = _ShapeCache(2)
         self.simt = False  # tests flip this to cross-check the tensor-core kernels on CUDA cores
         # consecutive 48->48 convs run as ONE persistent data-flow launch (ops.conv3x3_chain); LARVANET_B200_CHAIN=0
         # falls back to one launch per conv
         self.use_chain = os.environ.get('LARVANET_B200_CHAIN', '1') != '0'
         self._chain = None      # list of pending ConvArgs while a chain is being recorded
         self._chain_ws = {}     # (n, h, w) -> flag workspace
+        self._row_active = False  # the pass being recorded uses the row-marching kernel (ky-stacked operands)
+        self.row_min_pixels = int(os.environ.get('LARVANET_B200_ROW_MIN_PIXELS', str(96 * 1024)))
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (lv_launch_count only sees eager ones)
         # data parallel
         self.world_size = 1
         self.process_group = None
         self._symm = None       # symmetric-memory gradient exchange (data parallel), else NCCL
+        self._dp_optim = None   # FusedAdamW bound to this engine (enables the fused exchange+optimizer kernel)
+        self._dp_pending = False
 
     # ------------------------------------------------------------------ layers / packed weights
     def _enumerate_convs(self):
@@ -200,6 +251,24 @@ class LarvaEngine:
                 items_b.append(dict(w=w, packed=self._pk[(prefix, 'bwd', s)], transpose=1, i_off=C * s, i_cnt=C, cin=C,
                                     dtype=dt))
         self._pack_items_fwd, self._pack_items_bwd = items_f, items_b
+        # ky-stacked copies of the single-source operands for the row-marching kernel (csrc/conv_row.cu); refreshed
+        # lazily, only when a pass actually takes the row path
+        self._ky = None
+        if dt == torch.bfloat16:
+            single = [(p, O, I) for p, O, I in self._conv_layers if I == C and O == C]
+            nbytes = ops.packed_weight_bytes(C, C, dt)
+            step = (nbytes + 255) // 256 * 256
+            self._packed_ky = torch.zeros(2 * step * len(single), dtype=torch.uint8, device=self.device)
+            kf, kb = [], []
+            for k, (prefix, O, I) in enumerate(single):
+                w = self.arena.views[prefix + '.weight']
+                self._pk[(prefix, 'fwd', 'ky')] = self._packed_ky[2 * k * step:2 * k * step + nbytes]
+                self._pk[(prefix, 'bwd', 0, 'ky')] = self._packed_ky[(2 * k + 1) * step:(2 * k + 1) * step + nbytes]
+                kf.append(dict(w=w, packed=self._pk[(prefix, 'fwd', 'ky')], transpose=0, i_off=0, i_cnt=C, cin=C, dtype=dt,
+                               wlayout=_lib.LV_W_KY_STACKED))
+                kb.append(dict(w=w, packed=self._pk[(prefix, 'bwd', 0, 'ky')], transpose=1, i_off=0, i_cnt=C, cin=C, dtype=dt,
+                               wlayout=_lib.LV_W_KY_STACKED))
+            self._ky = dict(fwd=ops.build_pack_arrays(kf), all=ops.build_pack_arrays(kf + kb), version=None, bwd=False)
         # the optimizer can update the weights and emit both operand forms in ONE kernel (bf16, 48-output convs only)
         self._fused_convs = None
         if dt == torch.bfloat16 and os.environ.get('LARVANET_B200_FUSED_ADAMW', '1') != '0' and len(self._conv_layers) <= 64 \
@@ -221,8 +290,30 @@ class LarvaEngine:
         self._packed_version = self.arena.version()
         self._packed_bwd = backward
 
+    def repack_ky(self, backward=False):
+        """Refresh the ky-stacked operands of the row-marching kernel (only called by passes that take the row path)."""
+        ky = self._ky
+        if ky['version'] == self.arena.version() and ky['version'] is not None and (ky['bwd'] or not backward):
+            return
+        ops.pack_weights_prebuilt(ky['all'] if backward else ky['fwd'])
+        ky['version'], ky['bwd'] = self.arena.version(), backward
+
+    def use_row_path(self, n, h, w):
+        """Policy: the row-marching kernel (9 MMAs of N=144 per 128 px, tensor bound) needs jobs of several rows per SM to
+        amortise its two halo rows and fill its 128-pixel lanes; small problems (one 320x180 frame, 16 patches of 48x48:
+        2-3 tiles per SM, bound by the layer-to-layer hand-over latency, not by MMA throughput) stay on the 16x8-tile
+        kernel.  LARVANET_B200_ROW=0/1 forces either; default threshold from tools/row_vs_tile.py measurements."""
+        if self._ky is None or self.simt:
+            return False
+        mode = os.environ.get('LARVANET_B200_ROW', 'auto')
+        if mode in ('0', '1'):
+            return mode == '1'
+        return n * h * w >= self.row_min_pixels
+
     def mark_weights_changed(self):
         self._packed_version = None
+        if self._ky is not None:
+            self._ky['version'] = None
 
     def fused_update_available(self):
         return self._fused_convs is not None and not self.simt
@@ -245,14 +336,24 @@ class LarvaEngine:
 
     def _conv(self, srcs, prefix, out=None, **kw):
         _, b = self._w(prefix)
-        self._emit(ops.make_conv_args(srcs, self._pk[(prefix, 'fwd')], C, bias=b, out=out, **kw))
+        if self._row_active and len(srcs) == 1:
+            self._emit(ops.make_conv_args(srcs, self._pk[(prefix, 'fwd', 'ky')], C, bias=b, out=out,
+                                          wlayout=_lib.LV_W_KY_STACKED, **kw))
+        else:
+            self._emit(ops.make_conv_args(srcs, self._pk[(prefix, 'fwd')], C, bias=b, out=out, **kw))
 
     def _dgrad(self, dy, prefix, out, s=0, **kw):
-        self._emit(ops.make_conv_args([dy], self._pk[(prefix, 'bwd', s)], C, bias=None, out=out, **kw))
+        if self._row_active and (prefix, 'bwd', s, 'ky') in self._pk:
+            self._emit(ops.make_conv_args([dy], self._pk[(prefix, 'bwd', s, 'ky')], C, bias=None, out=out,
+                                          wlayout=_lib.LV_W_KY_STACKED, **kw))
+        else:
+            self._emit(ops.make_conv_args([dy], self._pk[(prefix, 'bwd', s)], C, bias=None, out=out, **kw))
 
     def _emit(self, args):
-        """Launch one conv, or queue it while a chain is being recorded (flushed by the first conv that cannot join)."""
-        if self._chain is not None and ops.chain_eligible(args):
+        """Launch one conv, or queue it while a chain is being recorded (flushed by the first conv that cannot join: another
+        shape, several sources, or the other weight layout -- a chain runs on ONE of the two chain kernels)."""
+        if self._chain is not None and ops.chain_eligible(args) and \
+                (not self._chain or self._chain[0].wlayout == args.wlayout):
             self._chain.append(args)
             return
         self._flush_chain()
@@ -292,9 +393,11 @@ class LarvaEngine:
         b.feats = [self._act(n, h, w) for _ in range(self.m)]
         b.u = self._act(n, h, w)
         b.mf = self._act(n, h, w) if self.v2 else None
+        b.row = self.use_row_path(n, h, w)
         return b
 
     def _run_infer(self, b, exit_leg=None):
+        self._row_active = b.row
         hw, hb = self._w('head.feature_extraction')
         k = self.m if exit_leg is None else exit_leg
         ops.head_bicubic(b.x, hw, hb, b.f0, b.base)
@@ -333,26 +436,14 @@ class LarvaEngine:
         n, _, h, w = (int(v) for v in x.shape)
         self.repack(backward=False)
         key = (n, h, w, exit_leg)
-        ent = self._infer.get(key)
-        if ent is None:
-            ent = [self._build_infer(n, h, w), None]
-            self._infer[key] = ent
-        b = ent[0]
+        ent = self._infer.get(key, lambda: self._build_infer(n, h, w))
+        b = ent['bufs']
+        if b.row:
+            self.repack_ky(backward=False)
         b.x.copy_(x.to(dtype=torch.float32), non_blocking=True)
         if n * h * w == 0:
             return b.out
-        if self.use_graphs and not self.simt:
-            if ent[1] is None:
-                g, nl = _capture_graph(lambda: self._run_infer(b, exit_leg))
-                ent[1] = g if g is not None else False
-                ent.append(nl)
-            if ent[1]:
-                ent[1].replay()
-                self.replayed_launches += ent[2]
-            else:
-                self._run_infer(b, exit_leg)
-        else:
-            self._run_infer(b, exit_leg)
+        _run_cached(self, ent, lambda: self._run_infer(b, exit_leg))
         return b.out
 
     # ------------------------------------------------------------------ training
@@ -362,7 +453,9 @@ class LarvaEngine:
         b.x = torch.empty((n, 3, h, w), dtype=torch.float32, device=dev)
         b.truth = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.float32, device=dev)
         b.base = torch.empty_like(b.truth)
-        b.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        # data parallel with the fused exchange+optimizer kernel: the local loss accumulator lives in the symmetric buffer
+        # (peers read it), the all-reduced loss lands in peers.loss_out
+        b.loss_sum = self._symm.loss_view if self._dp_fused() else torch.zeros(1, dtype=torch.float64, device=dev)
         b.f0 = self._act(n, h, w)
         b.t = [[self._act(n, h, w) for _ in range(nb)] for nb in self.blocks]       # post-ReLU of conv1
         b.a = [[self._act(n, h, w) for _ in range(nb - 1)] for nb in self.blocks]   # block outputs (not the last)
@@ -377,6 +470,7 @@ class LarvaEngine:
             b.mf, b.ut, b.gt, b.dut, b.dmf = (self._act(n, h, w) for _ in range(5))
             b.dfeat = [self._act(n, h, w) for _ in range(self.m)]
         b.exits = None
+        b.row = self.use_row_path(n, h, w)
         # weight-gradient batches, one per body (+ tail), in arena order
         numel = n * 3 * 16 * h * w
         denom = self.m + 1 if self.v2 else self.m
@@ -442,10 +536,18 @@ class LarvaEngine:
             if self._symm is not None:
                 self.arena.replace_grad(self._symm.buffer)
 
+    def _dp_fused(self):
+        """True when the data-parallel exchange is fused into the optimizer kernel (peer-mapped arenas on every rank, a
+        FusedAdamW attached, bf16 fused-update layout)."""
+        return (self.world_size > 1 and self._symm is not None and self._symm.peers is not None
+                and self._dp_optim is not None and self.fused_update_available()
+                and os.environ.get('LARVANET_B200_DP_FUSED', '1') != '0')
+
     def _run_train(self, b):
         """forward with saved activations + fused losses, then backward-data chain and batched weight gradients."""
+        self._row_active = b.row
         hw, hb = self._w('head.feature_extraction')
-        scale = b.scale / self.world_size
+        scale = b.scale
         b.loss_sum.zero_()
         if self.simt or self.act_dtype != torch.bfloat16:
             self.arena.grad.zero_()           # the CUDA-core weight-gradient kernels accumulate with atomics
@@ -516,32 +618,41 @@ class LarvaEngine:
             raise LarvaNetB200Error(f'truth shape {tuple(truth.shape)} does not match 4x input {tuple(x.shape)}')
         self.repack(backward=True)
         key = (n, h, w, bool(keep_exits))
-        ent = self._train.get(key)
-        if ent is None:
+
+        def build():
             b = self._build_train(n, h, w)
             if keep_exits:
                 b.exits = [torch.empty_like(b.truth) for _ in range(self.m + (1 if self.v2 else 0))]
-            scale = b.scale / self.world_size
+            # mean over the GLOBAL batch: 1 / (HR samples on all ranks x exits).  Ranks may hold different numbers of
+            # patches (dist.shard_range with total % world != 0), so the global count is all-reduced once per shape
+            # (collective: every rank builds its buffers for a new shape in the same step).
+            b.global_numel = float(n * 3 * 16 * h * w)
+            if self.world_size > 1:
+                import torch.distributed as tdist
+                cnt = torch.tensor([b.global_numel], dtype=torch.float64, device=self.device)
+                tdist.all_reduce(cnt, op=tdist.ReduceOp.SUM, group=self.process_group)
+                b.global_numel = float(cnt.item())
+            denom = self.m + 1 if self.v2 else self.m
+            b.scale = 1.0 / (b.global_numel * denom)
             for wb in b.wgrad:
-                wb.set_scale(scale)
-            ent = [b, None]
-            self._train[key] = ent
-        b = ent[0]
+                wb.set_scale(b.scale)
+            return b
+
+        ent = self._train.get(key, build)
+        b = ent['bufs']
+        if b.row:
+            self.repack_ky(backward=True)
         b.x.copy_(x, non_blocking=True)
         b.truth.copy_(truth, non_blocking=True)
-        if self.use_graphs and not self.simt:
-            if ent[1] is None:
-                g, nl = _capture_graph(lambda: self._run_train(b))
-                ent[1] = g if g is not None else False
-                ent.append(nl)
-            if ent[1]:
-                ent[1].replay()
-                self.replayed_launches += ent[2]
-            else:
-                self._run_train(b)
-        else:
-            self._run_train(b)
+        _run_cached(self, ent, lambda: self._run_train(b))
         self.arena.attach_grads()   # host-only book-keeping, after the launches so that the GPU is already busy
+        self.last_exits = b.exits
+        self._last_train = b
+        if self.world_size > 1 and self._dp_fused():
+            # the exchange happens inside the optimizer's kernel (ops.dp_adamw_pack_step): gradients AND the loss are
+            # global only after `optim.step()`; the returned scalar reads the all-reduced loss lazily
+            self._dp_pending = True
+            return DeviceScalar(self._symm.peers.loss_out, b.scale)
         if self.world_size > 1:
             from . import dist as lvdist
             if self._symm is not None:
@@ -552,11 +663,7 @@ class LarvaEngine:
                 works = lvdist.allreduce_gradients(self.arena.grad, b.loss_sum, self.process_group)
             for work in works:
                 work.wait()   # stream-ordered on NCCL: enqueues a wait on the current stream, no host sync
-        denom = self.m + 1 if self.v2 else self.m
-        numel = n * 3 * 16 * h * w * self.world_size
-        self.last_exits = b.exits
-        self._last_train = b
-        return DeviceScalar(b.loss_sum, 1.0 / (float(numel) * denom))
+        return DeviceScalar(b.loss_sum, b.scale)
 
     def saved_activations(self):
         """The forward activations the last train_step saved for its backward pass, as NCHW float32 CPU tensors keyed
@@ -584,6 +691,7 @@ class LarvaEngine:
     # (models/LarvaNet.py:102-107, validate_tree.py:94-96).  These helpers keep that surface: convert at the
     # boundary, run the same kernels eagerly.  Forward only (no autograd graph is recorded).
     def _to_act(self, x_nchw):
+        self._row_active = False   # individually-called modules run per-layer on the tile kernel
         x = x_nchw.detach().to(device=self.device, dtype=torch.float32).contiguous()
         n, c, h, w = (int(v) for v in x.shape)
         a = ops.act_empty(n, h, w, c, self.act_dtype, self.device)
@@ -697,8 +805,30 @@ class EdsrEngine:
             off += (b + 255) // 256 * 256
         self._pack_items = [dict(w=self.arena.views[p + '.weight'], packed=self._pk[p], transpose=0, i_off=0, i_cnt=i,
                                  cin=i, dtype=act_dtype) for p, o, i in self._layers]
+        # the F -> F convs of the body (32 resblock convs + after_res_conv) as ONE row-marching chain launch when the frame
+        # is large enough (csrc/conv_row.cu: 9 MMAs of N = 192 per 128 px instead of 27 of N = 64)
+        self._body = [p for p, o, i in self._layers if o == f and i == f]
+        self._row_ok = act_dtype == torch.bfloat16 and f in (48, 64)
+        if self._row_ok:
+            nb_ = ops.packed_weight_bytes(f, f, act_dtype)
+            step = (nb_ + 255) // 256 * 256
+            self._packed_ky = torch.zeros(step * len(self._body), dtype=torch.uint8, device=self.device)
+            for k, p in enumerate(self._body):
+                self._pk[(p, 'ky')] = self._packed_ky[k * step:k * step + nb_]
+            self._pack_items += [dict(w=self.arena.views[p + '.weight'], packed=self._pk[(p, 'ky')], transpose=0, i_off=0,
+                                      i_cnt=f, cin=f, dtype=act_dtype, wlayout=_lib.LV_W_KY_STACKED) for p in self._body]
+        self.row_min_pixels = int(os.environ.get('LARVANET_B200_ROW_MIN_PIXELS', str(96 * 1024)))
+        self._chain_ws = {}
         self._packed_version = None
-        self._infer = {}
+        self._infer = _ShapeCache(int(os.environ.get('LARVANET_B200_SHAPE_CACHE', '4')))
+
+    def use_row_path(self, n, h, w):
+        if not self._row_ok or self.simt:
+            return False
+        mode = os.environ.get('LARVANET_B200_ROW', 'auto')
+        if mode in ('0', '1'):
+            return mode == '1'
+        return n * h * w >= self.row_min_pixels
 
     def repack(self, force=False):
         ver = self.arena.version()
@@ -729,14 +859,30 @@ class EdsrEngine:
         ops.head_bicubic(b.x, v['first_conv.weight'], v['first_conv.bias'], b.x0, None,
                          pre_w=v['mean_shift.weight'], pre_b=v['mean_shift.bias'])
         a = b.x0
-        for j in range(self.nb):
-            p = f'res_blocks.{j}.body'
-            self._conv(a, p + '.0', f, out=b.t, relu=True)
-            dst = b.pp[j & 1]
-            self._conv(b.t, p + '.2', f, out=dst, res1=a, res_scale=self.res_weight)
-            a = dst
         skip = b.pp[self.nb & 1]
-        self._conv(a, 'after_res_conv', f, out=skip, res1=b.x0)
+        if self.use_row_path(*ops.act_dims(b.x0)[:3]):
+            KY = _lib.LV_W_KY_STACKED
+            mk = lambda src, p, **kw: ops.make_conv_args([src], self._pk[(p, 'ky')], f, bias=v[p + '.bias'], wlayout=KY, **kw)
+            chain = []
+            for j in range(self.nb):
+                p = f'res_blocks.{j}.body'
+                chain.append(mk(a, p + '.0', out=b.t, relu=True))
+                dst = b.pp[j & 1]
+                chain.append(mk(b.t, p + '.2', out=dst, res1=a, res_scale=self.res_weight))
+                a = dst
+            chain.append(mk(a, 'after_res_conv', out=skip, res1=b.x0))
+            n_, h_, w_, _ = ops.act_dims(b.x0)
+            if (n_, h_, w_) not in self._chain_ws:
+                self._chain_ws[(n_, h_, w_)] = ops.chain_workspace(n_, h_, w_, self.device)
+            ops.conv3x3_chain(chain, self._chain_ws[(n_, h_, w_)])
+        else:
+            for j in range(self.nb):
+                p = f'res_blocks.{j}.body'
+                self._conv(a, p + '.0', f, out=b.t, relu=True)
+                dst = b.pp[j & 1]
+                self._conv(b.t, p + '.2', f, out=dst, res1=a, res_scale=self.res_weight)
+                a = dst
+            self._conv(a, 'after_res_conv', f, out=skip, res1=b.x0)
         a = skip
         for s in range(self.nup):
             self._conv(a, f'upsample.body.{2 * s}', 4 * f, out=b.up[s], epilogue=_lib.LV_EPI_PS2_NHWC)
@@ -750,24 +896,10 @@ class EdsrEngine:
         n, _, h, w = (int(t) for t in x.shape)
         self.repack()
         key = (n, h, w)
-        ent = self._infer.get(key)
-        if ent is None:
-            ent = [self._build(n, h, w), None]
-            self._infer[key] = ent
-        b = ent[0]
+        ent = self._infer.get(key, lambda: self._build(n, h, w))
+        b = ent['bufs']
         b.x.copy_(x.to(dtype=torch.float32), non_blocking=True)
         if n * h * w == 0:
             return b.out
-        if self.use_graphs and not self.simt:
-            if ent[1] is None:
-                g, nl = _capture_graph(lambda: self._run(b))
-                ent[1] = g if g is not None else False
-                ent.append(nl)
-            if ent[1]:
-                ent[1].replay()
-                self.replayed_launches += ent[2]
-            else:
-                self._run(b)
-        else:
-            self._run(b)
+        _run_cached(self, ent, lambda: self._run(b))
         return b.out

@@ -249,8 +249,24 @@ def train_main(argv=None, epoch_bookkeeping=False):
     scale_list = [int(s) for s in args.scales.split(',')]
     os.makedirs(args.train_path, exist_ok=True)
 
+    # Data parallel (new; the reference is single-process): under torchrun every rank owns one GPU and a contiguous shard
+    # of `--batch_size` patches; the engine all-reduces the gradient arena so that the update equals the reference's
+    # single-process step on the global batch (models/LarvaNet.py:102-114).  Without torchrun this is a no-op.
+    from larvanet_b200 import dist as lvdist
+    rank, world, local = lvdist.init_from_env()
+    if world > 1:
+        torch.cuda.set_device(local)
+        if args.batch_size < world:
+            raise ValueError(f'--batch_size={args.batch_size} cannot be sharded over WORLD_SIZE={world} ranks')
+    shard_begin, shard_end = lvdist.shard_range(args.batch_size, rank, world)
+    local_batch = shard_end - shard_begin
+    log = print if rank == 0 else (lambda *a, **k: None)
+
     dataloader, dataloader_args, rest = _open_loader(args.dataloader, scale_list, rest)
     val_dataloader, _, _ = _open_loader(args.val_dataloader, scale_list)
+    if world > 1 and hasattr(dataloader, 'rs'):
+        # decorrelate the ranks' random crops (each rank draws its own shard of the global batch)
+        dataloader.rs = np.random.RandomState(int(getattr(dataloader_args, 'synthetic_seed', 0)) + 12345 + 7919 * rank)
 
     def before_prepare(m):
         m.volume_per_step = (args.input_patch_size ** 2) * args.batch_size * 3
@@ -260,16 +276,27 @@ def train_main(argv=None, epoch_bookkeeping=False):
     model, model_args = _open_model(args.model, rest, dict(is_training=True, scales=scale_list, global_step=args.global_step),
                                     before_prepare=before_prepare, restore=(args.restore_path, args.restore_target))
 
-    summary_writers = {s: _summary_writer(os.path.join(args.train_path, 'x%d' % s)) for s in scale_list}
-    with open(os.path.join(args.train_path, 'arguments.json'), 'w') as f:
-        f.write(json.dumps({**vars(args), **vars(dataloader_args), **vars(model_args)}, sort_keys=True, indent=2))
+    if world > 1:
+        # refuse to train N silent replicas: the plugin must be able to shard the step
+        engine = model._engine() if hasattr(model, '_engine') else None
+        if engine is None or not hasattr(engine, 'set_data_parallel'):
+            raise RuntimeError(f'--model={args.model} cannot run data-parallel (WORLD_SIZE={world}); launch it without torchrun')
+        engine.set_data_parallel(world)
+        model.dp_rank = rank
+        log(f'data parallel: {world} ranks x {local_batch} patches (global batch {args.batch_size}), gradient exchange: '
+            f'{"symmetric-memory peer kernel" if engine._symm is not None else "NCCL all-reduce"}')
+
+    summary_writers = {s: (_summary_writer(os.path.join(args.train_path, 'x%d' % s)) if rank == 0 else None) for s in scale_list}
+    if rank == 0:
+        with open(os.path.join(args.train_path, 'arguments.json'), 'w') as f:
+            f.write(json.dumps({**vars(args), **vars(dataloader_args), **vars(model_args)}, sort_keys=True, indent=2))
 
     if dataloader.is_threaded:
-        dataloader.start_training_queue_runner(batch_size=args.batch_size, input_patch_size=args.input_patch_size)
+        dataloader.start_training_queue_runner(batch_size=local_batch, input_patch_size=args.input_patch_size)
 
-    print('begin training')
-    print(f'volume {model.volume_per_step/1e6:.2f}M for 1 step.')
-    print(f'needs {model_args.val_volume/model.volume_per_step:.0f}steps to validate for {model_args.val_volume/1e9:.1f}G volume.')
+    log('begin training')
+    log(f'volume {model.volume_per_step/1e6:.2f}M for 1 step.')
+    log(f'needs {model_args.val_volume/model.volume_per_step:.0f}steps to validate for {model_args.val_volume/1e9:.1f}G volume.')
     loss = float('nan')
     import numpy as np
     from larvanet_b200.prefetch import DevicePrefetcher
@@ -281,7 +308,7 @@ def train_main(argv=None, epoch_bookkeeping=False):
             if dataloader.is_threaded:
                 input_list, truth_list = dataloader.get_queue_data(scale=sc)
             else:
-                input_list, truth_list = dataloader.get_patch_batch(batch_size=args.batch_size, scale=sc,
+                input_list, truth_list = dataloader.get_patch_batch(batch_size=local_batch, scale=sc,
                                                                     input_patch_size=args.input_patch_size)
             yield (torch.from_numpy(np.asarray(input_list, dtype=np.float32)).pin_memory(),
                    torch.from_numpy(np.asarray(truth_list, dtype=np.float32)).pin_memory())
@@ -303,16 +330,20 @@ def train_main(argv=None, epoch_bookkeeping=False):
             duration = time.time() - start_time
             if args.sleep_ratio > 0 and duration > 0:
                 time.sleep(min(10.0, duration * args.sleep_ratio))
-            if model.global_step < 1000 and model.global_step % args.log_freq == 0:
+            if rank == 0 and model.global_step < 1000 and model.global_step % args.log_freq == 0:
                 print('step %d, lr %.10f, loss %.6f (%.3f sec/batch)' % (model.global_step, model.get_lr(), loss, duration))
                 print(f'dataload_time:{dataload_time:.4f}s, np2ts_time:{np2ts_time:.4f}s, train_time: {train_time:.4f}s')
     except KeyboardInterrupt:
         print('interrupted (KeyboardInterrupt)')
 
-    print('finished')
+    log('finished')
     for w in summary_writers.values():
         if w is not None:
             w.close()
     if dataloader.is_threaded:
         dataloader.stop_queue_runners()
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
     return loss

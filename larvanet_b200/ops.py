@@ -170,8 +170,12 @@ def chain_workspace(n, h, w, device):
 
 def chain_eligible(args):
     """True when `args` (ConvArgs) can be a layer of `conv3x3_chain`."""
-    return (args.dtype == _lib.LV_BF16 and args.cin == 48 and args.num_src == 1 and args.cout == 48
-            and args.wlayout == _lib.LV_W_TAP_MAJOR)
+    if args.dtype != _lib.LV_BF16 or args.num_src != 1 or args.cin != args.cout:
+        return False
+    if args.wlayout == _lib.LV_W_KY_STACKED:      # row-marching chain: 48 or 64 channels, planar or PixelShuffle(4) epilogue
+        return args.cin in (48, 64) and (args.epilogue == _lib.LV_EPI_NHWC or
+                                         (args.epilogue == _lib.LV_EPI_PS4_NCHW and args.cin == 48))
+    return args.cin == 48
 
 
 def conv3x3_chain(arg_list, workspace, max_ctas=0):
@@ -192,7 +196,7 @@ def conv3x3_chain(arg_list, workspace, max_ctas=0):
         if CONV_TIMERS is not None:
             e1.record()
             a0 = arr[0]
-            CONV_TIMERS.append((e0, e1, 2.0 * 9 * 48 * 48 * a0.n * a0.h * a0.w * cnt, ('chain', cnt, 0)))
+            CONV_TIMERS.append((e0, e1, 2.0 * 9 * a0.cin * a0.cout * a0.n * a0.h * a0.w * cnt, ('chain', cnt, a0.wlayout)))
         pos += cnt
 
 
@@ -325,6 +329,17 @@ def adamw_pack_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, wei
                                          param.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                          float(weight_decay), int(step), float(grad_scale), arr, cnt, _stream()),
           'lv_adamw_pack_step')
+
+
+def dp_adamw_pack_step(param, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, fused, peers, grad_scale=1.0):
+    """Data-parallel optimizer step in one launch: gradient all-reduce over peer memory + AdamW + operand re-pack.
+    `peers` = larvanet_b200.dist.PeerArena (peer-mapped gradient arenas, flag blocks, loss slots, local control words)."""
+    arr, cnt = fused
+    check(_lib.load().lv_dp_adamw_pack_step(
+        _ptr(param, torch.float32, 'param'), _ptr(exp_avg, torch.float32, 'exp_avg'), _ptr(exp_avg_sq, torch.float32, 'exp_avg_sq'),
+        param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
+        arr, cnt, peers.grad_ptrs, peers.flag_ptrs, peers.loss_ptrs, peers.loss_out.data_ptr(), peers.ctl.data_ptr(),
+        int(peers.world), int(peers.rank), _stream()), 'lv_dp_adamw_pack_step')
 
 
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

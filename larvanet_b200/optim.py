@@ -31,6 +31,9 @@ class FusedAdamW(torch.optim.AdamW):
         if any(not p.requires_grad for p in engine.arena.params.values()):
             raise LarvaNetB200Error('FusedAdamW: frozen parameters inside the arena are not supported')
         self._engine = engine
+        if hasattr(engine, '_dp_optim'):
+            engine._dp_optim = self
+            engine._train.clear()      # buffers built before the optimizer was known use the unfused exchange
         self._exp_avg = torch.zeros_like(engine.arena.flat)
         self._exp_avg_sq = torch.zeros_like(engine.arena.flat)
 
@@ -48,6 +51,15 @@ class FusedAdamW(torch.optim.AdamW):
         g = self.param_groups[0]
         self._steps += 1
         a = self._engine.arena
+        if getattr(self._engine, '_dp_fused', lambda: False)():
+            # data parallel: gradient all-reduce over peer memory + update + re-pack in ONE kernel
+            if not self._engine._dp_pending:
+                raise LarvaNetB200Error('FusedAdamW.step() in data-parallel mode needs a preceding engine.train_step()')
+            self._engine._dp_pending = False
+            ops.dp_adamw_pack_step(a.flat, self._exp_avg, self._exp_avg_sq, g['lr'], g['betas'][0], g['betas'][1], g['eps'],
+                                   g['weight_decay'], self._steps, self._engine._fused_convs, self._engine._symm.peers, 1.0)
+            self._engine.weights_updated_and_packed()
+            return
         if getattr(self._engine, 'fused_update_available', lambda: False)():
             # update + re-pack of the conv operands (forward and backward-data forms) in one kernel
             ops.adamw_pack_step(a.flat, a.grad, self._exp_avg, self._exp_avg_sq, g['lr'], g['betas'][0], g['betas'][1],

@@ -128,6 +128,7 @@ class LarvaNetModule(nn.Module):
     """head -> body_0..body_{M-1} -> last leg (+ bicubic base) -- reference models/LarvaNet.py:270-293."""
 
     V2 = False
+    EARLY_EXIT = False
 
     def __init__(self, args):
         super().__init__()
@@ -144,6 +145,10 @@ class LarvaNetModule(nn.Module):
         self._wire()
         self._engine = None
         self.precision = getattr(args, 'precision', 'bf16')
+        # early-exit plugins only (reference models/LarvaLeg.py:275, models/LarvaLegV2.py:342): None = full network
+        self.leg = getattr(args, 'leg', None) if self.EARLY_EXIT else None
+        if self.leg is not None and not 0 <= self.leg <= self.len:
+            raise ValueError(f'--leg={self.leg} is outside 0..num_modules={self.len}')
 
     def _build_extra(self):
         pass
@@ -188,7 +193,9 @@ class LarvaNetModule(nn.Module):
 
     def forward(self, x):
         # fused path; result is a fresh tensor like the reference's (the engine's buffer is reused per call)
-        return self.engine().forward(x).clone()
+        # (early-exit plugins: leg == 0 returns the bicubic base, else bodies 0..leg-1 and that body's leg --
+        # reference models/LarvaLeg.py:289-299, models/LarvaLegV2.py:357-368)
+        return self.engine().forward(x, exit_leg=self.leg).clone()
 
 
 class LarvaNet(BaseModel):
@@ -198,20 +205,30 @@ class LarvaNet(BaseModel):
         super().__init__()
         self.volume_per_step = 0
 
+    # Flag defaults that differ between the reference's plugins (models/LarvaNet.py:47-66, models/LarvaNetV2.py:47-66,
+    # models/LarvaLeg.py:47-64, models/LarvaLegV2.py:47-67): subclasses override these class attributes.
+    DEFAULTS = dict(val_volume=30e9, lr=4e-4, min_lr=1e-8)
+    HAS_COOLDOWN = True      # --lr_step / --cooldown exist only in models/LarvaNet.py (:58,:63); elsewhere cooldown = 0
+    HAS_LEG = False          # --leg exists only in the LarvaLeg plugins (models/LarvaLeg.py:52)
+
     def parse_args(self, args):
         parser = argparse.ArgumentParser()
-        # same flags/defaults as reference models/LarvaNet.py:47-66
+        d = self.DEFAULTS
         parser.add_argument('--num_modules', type=int, default=2, help='Number of bodies (early exits).')
         parser.add_argument('--num_blocks', type=str, default=16, help='Residual blocks per body, comma separated.')
+        if self.HAS_LEG:
+            parser.add_argument('--leg', type=int, default=4, help='The early exit leg number, starts at 1.')
         parser.add_argument('--interpolate', type=str, default='bicubic', help='Interpolation of the base image.')
-        parser.add_argument('--val_volume', type=float, default=30e9, help='Training volume between validations.')
-        parser.add_argument('--lr', type=float, default=4e-4, help='Initial learning rate.')
+        parser.add_argument('--val_volume', type=float, default=d['val_volume'], help='Training volume between validations.')
+        parser.add_argument('--lr', type=float, default=d['lr'], help='Initial learning rate.')
         parser.add_argument('--lr_decay', type=float, default=0.5, help='Learning rate decay factor.')
-        parser.add_argument('--lr_step', type=int, default=20000, help='Learning rate decay step.')
+        if self.HAS_COOLDOWN:
+            parser.add_argument('--lr_step', type=int, default=20000, help='Learning rate decay step.')
         parser.add_argument('--threshold', type=float, default=0.001, help='Plateau threshold (absolute, dB).')
-        parser.add_argument('--min_lr', type=float, default=1e-8, help='Minimum learning rate.')
+        parser.add_argument('--min_lr', type=float, default=d['min_lr'], help='Minimum learning rate.')
         parser.add_argument('--patience', type=int, default=3, help='Plateau patience.')
-        parser.add_argument('--cooldown', type=int, default=6, help='Plateau cooldown.')
+        if self.HAS_COOLDOWN:
+            parser.add_argument('--cooldown', type=int, default=6, help='Plateau cooldown.')
         # larvanet_b200 extension (absent in the reference)
         parser.add_argument('--precision', type=str, default='bf16', choices=['bf16', 'fp32'],
                             help='bf16: tcgen05 tensor-core path; fp32: CUDA-core validation mode.')
@@ -238,7 +255,7 @@ class LarvaNet(BaseModel):
             self.optim = FusedAdamW([p for p in self.model.parameters() if p.requires_grad], lr=self.args.lr)
             self.scheduler = optim.lr_scheduler.ReduceLROnPlateau(
                 self.optim, mode='max', factor=self.args.lr_decay, patience=self.args.patience,
-                cooldown=self.args.cooldown, threshold=self.args.threshold, threshold_mode='abs', min_lr=self.args.min_lr)
+                cooldown=getattr(self.args, 'cooldown', 0), threshold=self.args.threshold, threshold_mode='abs', min_lr=self.args.min_lr)
         self.device = torch.device('cuda' if torch.cuda.is_available() else 'cpu')
         self.model = self.model.to(self.device)
 
@@ -263,8 +280,9 @@ class LarvaNet(BaseModel):
             self.total_volume += self.temp_volume
             self.temp_volume = 0
             self.validate_for_train(args, val_dataloader)
-            self.save(base_path=args.train_path)
-            print(f'saved a model checkpoint at volume {self.total_volume/1e9:.0f}G')
+            if getattr(self, 'dp_rank', 0) == 0:     # data parallel: every rank holds the same weights, one writes
+                self.save(base_path=args.train_path)
+                print(f'saved a model checkpoint at volume {self.total_volume/1e9:.0f}G')
             if summary is not None:
                 summary.add_scalar('loss', float(loss), self.global_step)
                 summary.add_scalar('lr', self.get_lr(), self.global_step)

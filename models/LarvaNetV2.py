@@ -49,3 +49,7 @@ class LarvaNetV2(LarvaNet):
         model_dict.update({k: v for k, v in pretrained.items() if k in model_dict})
         self.model.load_state_dict(model_dict)
         self.model.to(self.device)
+
+    # reference models/LarvaNetV2.py:47-66: other defaults than V1, no --lr_step / --cooldown (scheduler cooldown 0)
+    DEFAULTS = dict(val_volume=3e9, lr=1e-4, min_lr=1e-7)
+    HAS_COOLDOWN = False

@@ -30,7 +30,7 @@ def _import_reference():
             del sys.modules[name]
     sys.path.insert(0, REF)
     import importlib
-    mods = {n: importlib.import_module('models.' + n) for n in ('LarvaNet', 'LarvaNetV2', 'LarvaLeg', 'edsr')}
+    mods = {n: importlib.import_module('models.' + n) for n in ('LarvaNet', 'LarvaNetV2', 'LarvaLeg', 'LarvaLegV2', 'edsr')}
     sys.path.remove(REF)
     for name in list(sys.modules):
         if name == 'models' or name.startswith('models.') or name in ('validate', 'dataloaders', 'utils') \
@@ -96,15 +96,14 @@ def larva_case(mods, name, v2, blocks, n, h, w, seed, out_dir):
             store[f'exits_{tag}'] = np.stack(exits)
             store[f'feat_last_{tag}'] = feats[-1].detach().numpy()
         store[f'grad_summary_{tag}'] = np.stack([grad_summary(p.grad.numpy()) for _, p in m.named_parameters()])
-    if not v2:
-        # early exits: reference models/LarvaLeg.py:290-299 (--leg=k)
-        for k in range(len(blocks) + 1):
-            largs = types.SimpleNamespace(num_modules=len(blocks), num_blocks=args.num_blocks,
-                                          interpolate='bicubic', leg=k)
-            lm = mods['LarvaLeg'].LarvaNetModule(largs)
-            lm.load_state_dict(sd)
-            with torch.no_grad():
-                store[f'exit_leg{k}_f32'] = lm(torch.from_numpy(lr)).numpy()
+    # early exits: reference models/LarvaLeg.py:290-299 and models/LarvaLegV2.py:357-368 (--leg=k)
+    for k in range(len(blocks) + 1):
+        largs = types.SimpleNamespace(num_modules=len(blocks), num_blocks=args.num_blocks,
+                                      interpolate='bicubic', leg=k)
+        lm = mods['LarvaLegV2' if v2 else 'LarvaLeg'].LarvaNetModule(largs)
+        lm.load_state_dict(sd)
+        with torch.no_grad():
+            store[f'exit_leg{k}_f32'] = lm(torch.from_numpy(lr)).numpy()
     np.savez_compressed(os.path.join(out_dir, name + '.npz'), **store)
     print('wrote', name, 'loss', store['loss_f32'])
 

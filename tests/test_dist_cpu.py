@@ -89,3 +89,36 @@ def test_symmetric_exchange_falls_back_collectively(tmp_path):
     got = np.load(out)
     assert bool(got['none'][0])
     np.testing.assert_array_equal(got['flat'], np.full(8, 3.0, dtype=np.float32))
+
+
+def _symm_asym_worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    lvdist.init_from_env('gloo')
+    entered = []
+
+    # rank 0 "allocates" fine, rank 1's local allocation throws: rank 0 must NOT enter the rendezvous alone
+    def fake_init(self, numel, device, group=None):
+        if rank == 1:
+            raise MemoryError('simulated symm_mem.empty failure on one rank')
+        self.buffer = torch.zeros(8)
+
+    def fake_rendezvous(self):
+        entered.append(rank)
+        raise AssertionError('rendezvous entered although a peer failed to allocate')
+
+    lvdist.SymmetricGradExchange.__init__ = fake_init
+    lvdist.SymmetricGradExchange.rendezvous = fake_rendezvous
+    ex = lvdist.SymmetricGradExchange.try_create(1000, torch.device('cpu'))
+    ok = torch.tensor([1 if (ex is None and not entered) else 0], dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.savez(out_path, ok=ok.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_symmetric_exchange_one_rank_allocation_failure_does_not_deadlock(tmp_path):
+    out = str(tmp_path / 'asym.npz')
+    mp.spawn(_symm_asym_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert int(np.load(out)['ok'][0]) == 1

@@ -4,6 +4,8 @@ Every test feeds the CUDA kernel and the numpy oracle the SAME operands (for bf1
 values as float64), so the only differences are fp32-vs-fp64 accumulation and the final store rounding:
   bf16 store: |err| <= 2^-8 * |ref| + small abs;   fp32 mode: <= 1e-5 relative.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -262,7 +264,8 @@ def test_errors_are_loud():
 @pytest.mark.parametrize('shape', [(1, 14, 8), (2, 19, 13), (1, 5, 3), (3, 48, 48), (1, 33, 70), (1, 180, 320)])
 @pytest.mark.parametrize('simt', [False, True])
 def test_conv48_ky_stacked_layout(shape, simt):
-    """The ky-stacked tensor-core kernel (9 MMAs of N=144, row-shift epilogue) against the oracle, all epilogue paths."""
+    """The row-marching tensor-core kernel (ky-stacked weights: 9 MMAs of N=144 per 128 px of a row, vertical taps summed
+    in TMEM; csrc/conv_row.cu) against the oracle, all epilogue paths."""
     dtype = torch.bfloat16
     n, h, w = shape
     rs = np.random.RandomState(7000 + 31 * h + w)
@@ -299,28 +302,73 @@ def test_conv48_ky_stacked_layout(shape, simt):
         np.testing.assert_allclose(from_nhwc(dx), dx_ref, rtol=rtol, atol=atol)
 
 
-def test_conv_ky_stacked_multi_source():
+def test_conv_ky_stacked_multi_source_is_rejected():
+    """The row-marching kernel keeps ONE layer's weights resident: multi-source convs (V2 merge) stay on the tap-major
+    kernel and asking for the ky-stacked layout fails loudly instead of computing something else."""
     dtype = torch.bfloat16
-    n, h, w = 1, 30, 20
     rs = np.random.RandomState(77)
     wt, b, wq = _rand_conv(rs, 48, 192, dtype)
-    srcs, srcq = zip(*[_act(rs, n, 48, h, w, dtype) for _ in range(4)])
+    srcs, _ = zip(*[_act(rs, 1, 48, 30, 20, dtype) for _ in range(4)])
     packed = _pack(wt, dtype, 48, wlayout=_lib.LV_W_KY_STACKED)
-    out = torch.empty_like(srcs[0])
-    ops.conv3x3(list(srcs), packed, 48, bias=torch.from_numpy(b).cuda(), out=out, wlayout=_lib.LV_W_KY_STACKED)
-    ref = O.conv2d(np.concatenate(srcq, axis=1), wq, b.astype(np.float64))
+    if os.environ.get('LARVANET_B200_EXPERIMENTAL') == '1':
+        pytest.skip('experimental build routes this shape to tools/experiments/conv_tc_ky.cu')
+    with pytest.raises(_lib.LarvaNetB200Error):
+        ops.conv3x3(list(srcs), packed, 48, bias=torch.from_numpy(b).cuda(), out=torch.empty_like(srcs[0]),
+                    wlayout=_lib.LV_W_KY_STACKED)
+
+
+@pytest.mark.parametrize('shape', [(1, 12, 16), (2, 19, 13), (1, 3, 130), (3, 40, 40), (1, 70, 200)])
+def test_conv64_row_kernel(shape):
+    """EDSR's 64 -> 64 convs on the row-marching kernel (8-block accumulator ring, N = 192): ReLU and residual epilogues
+    against the oracle on bf16-rounded operands."""
+    dtype = torch.bfloat16
+    n, h, w = shape
+    rs = np.random.RandomState(6400 + 31 * h + w)
+    wt, b, wq = _rand_conv(rs, 64, 64, dtype, wscale=0.04)
+    x, xq = _act(rs, n, 64, h, w, dtype)
+    r1, r1q = _act(rs, n, 64, h, w, dtype)
+    packed = _pack(wt, dtype, 64, wlayout=_lib.LV_W_KY_STACKED)
+    bt = torch.from_numpy(b).cuda()
     rtol, atol = _tol(dtype)
-    np.testing.assert_allclose(from_nhwc(out), ref, rtol=rtol, atol=atol * 2)
+    conv = O.conv2d(xq, wq, b.astype(np.float64))
+    out = torch.empty_like(x)
+    ops.conv3x3([x], packed, 64, bias=bt, out=out, relu=True, wlayout=_lib.LV_W_KY_STACKED)
+    np.testing.assert_allclose(from_nhwc(out), np.maximum(conv, 0), rtol=rtol, atol=atol)
+    out2 = torch.empty_like(x)
+    ops.conv3x3([x], packed, 64, bias=bt, out=out2, res1=r1, wlayout=_lib.LV_W_KY_STACKED)
+    np.testing.assert_allclose(from_nhwc(out2), conv + r1q, rtol=rtol, atol=atol)
+    out3 = torch.empty_like(x)          # res_scale != 1 takes the generic epilogue
+    ops.conv3x3([x], packed, 64, bias=bt, out=out3, res1=r1, res_scale=0.5, wlayout=_lib.LV_W_KY_STACKED)
+    np.testing.assert_allclose(from_nhwc(out3), 0.5 * conv + r1q, rtol=rtol, atol=atol)
 
 
-def _chain_layers(rs, n, h, w, depth):
+@pytest.mark.parametrize('shape', [(1, 270, 480), (8, 64, 64), (16, 48, 48), (1, 1, 1), (1, 2, 127), (1, 129, 128), (2, 11, 128)])
+def test_row_kernel_equals_tap_major_kernel_at_size(shape):
+    """Row-marching kernel vs the tap-major tensor-core kernel on identical operands at BASELINE frame / batch sizes and
+    at the lane-boundary widths (127 / 128 px, 1-row images): same products, different fp32 summation order."""
+    dtype = torch.bfloat16
+    n, h, w = shape
+    rs = np.random.RandomState(9100 + h + w)
+    wt, b, _ = _rand_conv(rs, 48, 48, dtype)
+    x, _ = _act(rs, n, 48, h, w, dtype)
+    r1, _ = _act(rs, n, 48, h, w, dtype)
+    bt = torch.from_numpy(b).cuda()
+    a, ref = torch.empty_like(x), torch.empty_like(x)
+    ops.conv3x3([x], _pack(wt, dtype, 48, wlayout=_lib.LV_W_KY_STACKED), 48, bias=bt, out=a, relu=True, res1=r1,
+                wlayout=_lib.LV_W_KY_STACKED)
+    ops.conv3x3([x], _pack(wt, dtype, 48), 48, bias=bt, out=ref, relu=True, res1=r1)
+    d = (a.float() - ref.float()).abs()
+    assert d.max().item() <= 0.0625 and (d > 0).float().mean().item() < 0.05     # rare 1-ulp bf16 flips only
+
+
+def _chain_layers(rs, n, h, w, depth, wlayout=0):
     """A LarvaNet-like layer list on ping-pong buffers: resblocks (relu conv, conv + skips), a leg with PixelShuffle +
     loss epilogue, and masked input-gradient style layers.  Returns (make_args(bufs) -> [ConvArgs], make_bufs)."""
     dtype = torch.bfloat16
     convs = []
     for _ in range(8):
         wt, b, _ = _rand_conv(rs, 48, 48, dtype, wscale=0.04)
-        convs.append((_pack(wt, dtype, 48), torch.from_numpy(b).cuda()))
+        convs.append((_pack(wt, dtype, 48, wlayout=wlayout), torch.from_numpy(b).cuda()))
     x0, _ = _act(rs, n, 48, h, w, dtype)
     base = torch.from_numpy(rs.uniform(0, 255, (n, 3, 4 * h, 4 * w)).astype(np.float32)).cuda()
     truth = torch.from_numpy(rs.uniform(0, 255, (n, 3, 4 * h, 4 * w)).astype(np.float32)).cuda()
@@ -332,7 +380,8 @@ def _chain_layers(rs, n, h, w, depth):
 
     def make_args(B):
         L = []
-        cv = lambda i, src, **kw: L.append(ops.make_conv_args([src], convs[i % 8][0], 48, bias=convs[i % 8][1], **kw))
+        cv = lambda i, src, **kw: L.append(ops.make_conv_args([src], convs[i % 8][0], 48, bias=convs[i % 8][1],
+                                                              wlayout=wlayout, **kw))
         cur, nxt = B['x'], B['a']
         for blk in range(depth):
             cv(2 * blk, cur, out=B['t'], relu=True)                                     # t is rewritten every block (WAR)
@@ -347,14 +396,16 @@ def _chain_layers(rs, n, h, w, depth):
     return make_args, make_bufs
 
 
+@pytest.mark.parametrize('wlayout', [0, 1], ids=['tile_chain', 'row_chain'])
 @pytest.mark.parametrize('shape,ctas', [((2, 37, 45), 0), ((16, 48, 48), 0), ((1, 180, 320), 0), ((3, 20, 9), 5),
-                                        ((1, 16, 8), 0)])
-def test_conv_chain_matches_sequential(shape, ctas):
-    """lv_conv3x3_chain (one persistent data-flow launch) == the same layers launched one by one, bit for bit; repeated
-    launches reuse the self-cleaning flag workspace."""
+                                        ((1, 16, 8), 0), ((2, 135, 240), 0)])
+def test_conv_chain_matches_sequential(shape, ctas, wlayout):
+    """lv_conv3x3_chain (one persistent data-flow launch; tap-major weights -> 16x8-tile kernel, ky-stacked weights ->
+    row-marching kernel) == the same layers launched one by one, bit for bit; repeated launches reuse the self-cleaning
+    flag workspace."""
     n, h, w = shape
     rs = np.random.RandomState(5)
-    make_args, make_bufs = _chain_layers(rs, n, h, w, depth=5)
+    make_args, make_bufs = _chain_layers(rs, n, h, w, depth=5, wlayout=wlayout)
     ref = make_bufs()
     for a in make_args(ref):
         ops.conv3x3_launch(a)
@@ -406,6 +457,8 @@ def test_uint8_and_psnr_helpers():
     assert abs(psnr - O.image_psnr(o8, t8)) < 1e-4
 
 
+@pytest.mark.skipif(os.environ.get('LARVANET_B200_EXPERIMENTAL') != '1',
+                    reason='tools/experiments kernels are only built with LARVANET_B200_EXPERIMENTAL=1')
 def test_cluster_resident_strip_chain_is_bit_exact():
     """The opt-in cluster-resident chain (conv_strip.cu, LARVANET_B200_STRIP=1: activations in shared memory, halo columns
     through DSMEM) must give the per-layer launches' results bit for bit.  Runs in a subprocess: the switch is read once."""

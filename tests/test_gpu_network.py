@@ -185,6 +185,27 @@ def test_early_exit_matches_reference(golden_dir):
         np.testing.assert_allclose(out, g[f'exit_leg{k}_f32'], rtol=1e-4, atol=1e-4 * 255)
 
 
+@pytest.mark.parametrize('name', ['larvanet_m3_b111', 'larvanetv2_m2_b11', 'larvanetv2_m4_b1111'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_leg_plugins_match_reference_golden(golden_dir, name, precision):
+    """`--model=LarvaLeg|LarvaLegV2 --leg=k` (reference models/LarvaLeg.py:289-299, models/LarvaLegV2.py:357-368)
+    through the plugin call, every k in 0..M, against outputs of the reference's own LarvaLeg modules."""
+    g, v2, blocks, params, lr, hr = _case(golden_dir, name)
+    for k in range(len(blocks) + 1):
+        mod = importlib.import_module('models.LarvaLegV2' if v2 else 'models.LarvaLeg')
+        m = mod.create_model()
+        m.parse_args([f'--num_modules={len(blocks)}', '--num_blocks=' + ','.join(map(str, blocks)), f'--leg={k}',
+                      f'--precision={precision}'])
+        m.prepare(is_training=False, scales=[4])
+        load_params(m.get_model(), params)
+        out = m.upscale(list(lr), 4)
+        ref = g[f'exit_leg{k}_f32']
+        if precision == 'fp32':
+            np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4 * 255)
+        else:
+            assert np.max(np.abs(out - ref)) <= 2.0
+
+
 @pytest.mark.parametrize('shape', [(1, 180, 320), (4, 48, 48)])
 def test_tensor_core_path_equals_cuda_core_path_at_full_size(shape):
     """BASELINE config sizes: the tcgen05 chain vs the CUDA-core chain on identical bf16 operands (size-independent

@@ -158,9 +158,15 @@ def test_edsr_plugin_surface():
 def test_workspace_size_queries_need_no_gpu():
     """Pure host arithmetic of the C-ABI: chain flag workspace and the stream-K style weight-gradient schedule."""
     lib = _lib.load()
-    assert lib.lv_conv_chain_workspace_bytes(16, 48, 48) == (16 * 3 * 6 + 1) * 4
-    assert lib.lv_conv_chain_workspace_bytes(1, 180, 320) == (12 * 40 + 1) * 4
-    assert lib.lv_conv_chain_workspace_bytes(0, 48, 48) == 4
+    # one workspace serves both chain kernels: max(16x8 tile flags, row-job flags at 1 row per job) + exit counter
+    def ws(n, h, w):
+        tiles = n * -(-h // 16) * -(-w // 8)
+        strips = max(1, -(-(n * (w + 1) - 1) // 128))
+        return (max(tiles, strips * max(h, 1)) + 1) * 4
+    assert lib.lv_conv_chain_workspace_bytes(16, 48, 48) == ws(16, 48, 48) == (7 * 48 + 1) * 4
+    assert lib.lv_conv_chain_workspace_bytes(1, 180, 320) == ws(1, 180, 320) == (3 * 180 + 1) * 4
+    assert lib.lv_conv_chain_workspace_bytes(8, 270, 480) == ws(8, 270, 480)
+    assert lib.lv_conv_chain_workspace_bytes(0, 48, 48) == ws(0, 48, 48)
     slot = 448 * 128 * 4                      # accumulator columns x TMEM lanes x fp32
 
     def items(shapes):
@@ -190,3 +196,51 @@ def test_device_scalar_reads_lazily():
     assert s.item() == 3.0 and float(s) == 3.0
     acc[0] = 20.0                                  # read at call time, not at construction
     assert s.item() == 5.0 and float(s.tensor()) == 5.0
+
+
+# defaults of every wrapper flag, transcribed from the reference (models/LarvaNet.py:47-66, models/LarvaNetV2.py:47-66,
+# models/LarvaLeg.py:47-64, models/LarvaLegV2.py:47-67); when the reference modules are importable (oracle/_ref or
+# /root/reference) the table itself is checked against them below
+REFERENCE_DEFAULTS = {
+    'LarvaNet': dict(num_modules=2, num_blocks=16, interpolate='bicubic', val_volume=30e9, lr=4e-4, lr_decay=0.5,
+                     lr_step=20000, threshold=0.001, min_lr=1e-8, patience=3, cooldown=6),
+    'LarvaNetV2': dict(num_modules=2, num_blocks=16, interpolate='bicubic', val_volume=3e9, lr=1e-4, lr_decay=0.5,
+                       threshold=0.001, min_lr=1e-7, patience=3),
+    'LarvaLeg': dict(num_modules=2, num_blocks=16, leg=4, interpolate='bicubic', val_volume=3e9, lr=1e-4, lr_decay=0.5,
+                     threshold=0.001, min_lr=1e-7, patience=3),
+    'LarvaLegV2': dict(num_modules=2, num_blocks=16, leg=4, interpolate='bicubic', val_volume=3e9, lr=1e-4,
+                       lr_decay=0.5, threshold=0.001, min_lr=1e-7, patience=3),
+}
+
+
+@pytest.mark.parametrize('modname', sorted(REFERENCE_DEFAULTS))
+def test_plugin_flag_defaults_match_reference(modname):
+    m = importlib.import_module('models.' + modname).create_model()
+    args, _ = m.parse_args([])
+    ours = {k: v for k, v in vars(args).items() if k != 'precision'}     # --precision is this repo's extension
+    assert ours == REFERENCE_DEFAULTS[modname]
+    from oracle import ref_loader
+    mods = ref_loader.load()
+    if mods is not None:                                                 # the table above == the reference's own parser
+        ref_args, _ = mods[modname].create_model().parse_args([])
+        assert vars(ref_args) == REFERENCE_DEFAULTS[modname]
+    # scheduler: cooldown only where the reference has the flag (models/LarvaNet.py:90-92 vs models/LarvaNetV2.py:86-88)
+    m.parse_args(['--num_modules=1', '--num_blocks=1'] + (['--leg=1'] if 'Leg' in modname else []))
+    m.prepare(is_training=True, scales=[4])
+    assert m.scheduler.cooldown == (6 if modname == 'LarvaNet' else 0)
+    assert m.scheduler.patience == 3 and m.scheduler.factor == 0.5 and m.scheduler.mode == 'max'
+    assert m.scheduler.min_lrs == [REFERENCE_DEFAULTS[modname]['min_lr']]
+
+
+@pytest.mark.parametrize('modname,v2', [('LarvaLeg', False), ('LarvaLegV2', True)])
+def test_leg_plugins_share_the_state_dict_and_validate_leg(modname, v2):
+    m = importlib.import_module('models.' + modname).create_model()
+    args, rest = m.parse_args(['--num_modules=3', '--num_blocks=1,1,1', '--leg=2', '--x'])
+    assert rest == ['--x'] and args.leg == 2
+    m.prepare(is_training=False, scales=[4])
+    assert m.get_model().leg == 2
+    assert list(m.get_model().state_dict().keys()) == list(synth.larva_param_shapes([1, 1, 1], v2=v2).keys())
+    bad = importlib.import_module('models.' + modname).create_model()
+    bad.parse_args(['--num_modules=2', '--num_blocks=1,1', '--leg=3'])
+    with pytest.raises(ValueError):
+        bad.prepare(is_training=False, scales=[4])

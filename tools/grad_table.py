@@ -25,7 +25,7 @@ def main():
         print(f'{n:45s} rel={np.linalg.norm(g-r)/np.linalg.norm(r):.4f} |ref|={np.linalg.norm(r):.3e} |got|={np.linalg.norm(g):.3e} '
               f'cos={np.sum(g*r)/np.linalg.norm(g)/np.linalg.norm(r):.5f}')
     # head: compare against oracle head wgrad using the DEVICE dfin (isolates the head wgrad kernel)
-    b = eng._train[(2, 12, 10, True)][0]
+    b = eng._train.entries[(2, 12, 10, True)]['bufs']
     # planar-8 [n, h, c/8, w, 8] -> NCHW
     dfin = b.dfin[0].float().cpu().permute(0, 2, 4, 1, 3).reshape(2, 48, 12, 10).numpy().astype(np.float64)
     _, dwh, dbh = O.conv2d_backward(lr.astype(np.float64), np.zeros((48, 3, 3, 3)), dfin)
