@@ -90,6 +90,18 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
+def roofline_traffic(kernel_substr):
+    path = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
+    try:
+        with open(path) as f:
+            for rec in json.load(f):
+                if kernel_substr in rec.get('kernel', ''):
+                    return rec.get('dram_bytes_per_launch')
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def measured_peaks():
     path = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -100,18 +112,37 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def headline_config(world):
+    """The `config` object of the headline line -- shared by both arms so that the driver's same-config check holds."""
+    return {'workload': 'LarvaNet x4 training step, batch 16 per GPU, 48x48 LR patches, L1 multi-exit loss, '
+                        'M=4 B=4,4,4,4, AdamW (BASELINE.json configs[1])',
+            'global_batch': BATCH * world, 'parallelism': f'dp{world}',
+            'l2': 'inputs rotate over 8 resident batches; saved activations+gradients (~330 MB/step) exceed the 126 MB L2'}
+
+
+def _cpu_trainer(blocks, v2=False, lr=4e-4, threads=None):
+    """The reference's train step on the host: the UNMODIFIED reference modules when oracle/_ref is staged (kind
+    "reference"), else the golden-pinned restatement oracle/torch_port.py (kind "port")."""
+    from larvanet_b200 import synth
+    from oracle import ref_loader, torch_port
+    params = synth.make_larva_params(blocks, v2=v2, seed=0)
+    if ref_loader.load() is not None:
+        return ref_loader.RefTrainer(params, blocks, v2=v2, lr=lr), 'reference', 'reference modules via oracle/ref_loader.py'
+    return torch_port.CpuTrainer(params, blocks, v2=v2, lr=lr, threads=threads), 'port', 'oracle/torch_port.py'
+
+
 def run_reference(a):
-    """CPU arm: the PyTorch-CPU port of the reference train step on all host threads (rank 0 only)."""
+    """CPU arm: the reference's own train step (its modules + torch.optim.AdamW, fp32) on all host threads, rank 0 only,
+    on the headline config (global batch = 16 x --gpus, like our arm's weak scaling)."""
     if int(os.environ.get('RANK', '0')) != 0:
         return
     import torch
     from larvanet_b200 import synth
-    from oracle import torch_port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = synth.make_larva_params(BLOCKS, seed=0)
-    tr = torch_port.CpuTrainer(params, BLOCKS, lr=4e-4, threads=cores)
-    lr, hr = synth.make_images(BATCH, PATCH, PATCH, seed=1)
+    tr, kind, what = _cpu_trainer(BLOCKS, threads=cores)
+    gb = BATCH * max(1, a.gpus)
+    lr, hr = synth.make_images(gb, PATCH, PATCH, seed=1)
     x, t = torch.from_numpy(lr), torch.from_numpy(hr)
     for _ in range(max(1, min(a.warmup, 2))):
         tr.step(x, t)
@@ -119,15 +150,15 @@ def run_reference(a):
     for _ in range(a.steps):
         tr.step(x, t)
     dt = time.perf_counter() - t0
-    v = BATCH * a.steps / dt
+    v = gb * a.steps / dt
+    cfg = headline_config(max(1, a.gpus))
     line = {
         'impl': 'reference', 'metric': 'train_patches_per_s', 'value': v, 'unit': 'patches/s', 'n_gpus': a.gpus,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': dt / a.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'LarvaNet x4 training step, batch 16, 48x48 LR patches, L1 multi-exit loss '
-                               '(M=4, B=4,4,4,4), AdamW', 'device': 'host CPU'},
-        'cpu_baseline': {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{a.steps} full steps of batch {BATCH} (oracle/torch_port.py, torch CPU fp32)'},
+        'config': cfg,
+        'cpu_baseline': {'value': v, 'unit': 'patches/s', 'cores': cores, 'kind': kind,
+                         'sample': f'{a.steps} full steps of batch {gb} on the host CPU ({what}, torch CPU fp32)'},
         'e2e': {'value': v, 'unit': 'patches/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -136,14 +167,12 @@ def run_reference(a):
 
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_baseline_sample(budget_s=20.0):
-    """Bounded CPU sample on this box's host cores (rank 0, N=1): reference port, train step and 720p inference."""
+    """Bounded CPU sample on this box's host cores (rank 0, N=1): the reference's train step and 720p inference."""
     import torch
     from larvanet_b200 import synth
-    from oracle import torch_port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    params = synth.make_larva_params(BLOCKS, seed=0)
-    tr = torch_port.CpuTrainer(params, BLOCKS, lr=4e-4, threads=cores)
+    tr, kind, what = _cpu_trainer(BLOCKS, threads=cores)
     lr, hr = synth.make_images(BATCH, PATCH, PATCH, seed=1)
     x, t = torch.from_numpy(lr), torch.from_numpy(hr)
     tr.step(x, t)
@@ -159,9 +188,63 @@ def cpu_baseline_sample(budget_s=20.0):
         tr.infer(xi)
         m += 1
     infer = (16 * INF_H * INF_W) * m / (time.perf_counter() - t0) / 1e6
-    return {'value': train, 'unit': 'patches/s', 'cores': cores, 'kind': 'port',
-            'sample': f'{n} train steps of batch {BATCH} + {m} 720p frames, torch CPU fp32 (oracle/torch_port.py)',
+    return {'value': train, 'unit': 'patches/s', 'cores': cores, 'kind': kind,
+            'sample': f'{n} train steps of batch {BATCH} + {m} 720p frames, torch CPU fp32 ({what})',
             'inference_mpix_s': infer}
+
+
+def gpu_library_baseline(dev, steps=20):
+    """The library kernels to beat: the reference's modules on THIS B200 through stock PyTorch / cuDNN --
+    eager fp32 (TF32 off), TF32, and bf16 autocast + channels_last -- CUDA-event timed like reference runtime.py:61-67
+    (synchronise, time, synchronise).  cfg2 train step (patches/s) and cfg1 720p inference (Mpix/s)."""
+    import torch
+    from larvanet_b200 import synth
+    from oracle import ref_loader, torch_port
+    params = synth.make_larva_params(BLOCKS, seed=0)
+    lr, hr = synth.make_images(BATCH, PATCH, PATCH, seed=1)
+    x720 = torch.from_numpy(synth.make_images(1, INF_H, INF_W, seed=1)[0]).to(dev)
+    out = {'what': 'reference modules (oracle/_ref) on the same GPU, stock torch ' + torch.__version__ + ' / cuDNN kernels, '
+                   'cudnn.benchmark on' if ref_loader.load() is not None else 'oracle/torch_port.py on the same GPU',
+           'modes': {}}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32, ac, cl in (('fp32', False, None, False), ('tf32', True, None, False),
+                                   ('bf16_autocast_channels_last', True, torch.bfloat16, True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            if ref_loader.load() is not None:
+                tr = ref_loader.RefTrainer(params, BLOCKS, lr=4e-4, device=dev, autocast_dtype=ac, channels_last=cl)
+                step = lambda a, b: tr.step(a, b, sync=False)
+                infer = tr.infer
+            else:
+                if ac is not None:
+                    continue
+                tp = torch_port.CpuTrainer({k: v for k, v in params.items()}, BLOCKS, lr=4e-4)
+                tp.p = {k: v.detach().to(dev).requires_grad_(True) for k, v in tp.p.items()}
+                tp.optim = torch.optim.AdamW(list(tp.p.values()), lr=4e-4)
+                step, infer = tp.step, tp.infer
+            x, t = torch.from_numpy(lr).to(dev), torch.from_numpy(hr).to(dev)
+            xi = x720
+            if cl:
+                x, xi = x.contiguous(memory_format=torch.channels_last), x720.contiguous(memory_format=torch.channels_last)
+            res = {}
+            for what, fn, units in (('train_patches_per_s', lambda: step(x, t), BATCH),
+                                    ('infer_720p_mpix_per_s', lambda: infer(xi), 16 * INF_H * INF_W / 1e6)):
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                res[what] = units * steps / (e0.elapsed_time(e1) * 1e-3)
+            out['modes'][name] = res
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return out
 
 
 def run_ours(a):
@@ -212,19 +295,20 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     counts = {}
+    engines = [eng]
 
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
         barrier()
-        counts['c0'], counts['r0'] = _lib.launch_count(), eng.replayed_launches
+        counts['c0'], counts['r0'] = _lib.launch_count(), sum(e.replayed_launches for e in engines)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(warmup + i)
         e1.record()
         barrier()
-        counts['n'] = (_lib.launch_count() - counts['c0']) + (eng.replayed_launches - counts['r0'])
+        counts['n'] = (_lib.launch_count() - counts['c0']) + (sum(e.replayed_launches for e in engines) - counts['r0'])
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -238,6 +322,9 @@ def run_ours(a):
     clocks = sampler.stop() if rank == 0 else None
     launches = counts['n']
     value = BATCH * world * a.steps / (ms * 1e-3)
+    # the driver may ask for a very short timed region (20 steps = 11 ms): also time a long one and report both
+    long_steps = max(200, a.steps)
+    ms_long = timed(step_resident, long_steps, 2) if long_steps > a.steps else ms
 
     # ---- e2e through the plugin API with host batches
     args_ns = types.SimpleNamespace(train_path='/tmp')
@@ -266,14 +353,16 @@ def run_ours(a):
         'metric': 'train_patches_per_s', 'value': value, 'unit': 'patches/s', 'n_gpus': world, 'steps': a.steps,
         'warmup': warm, 'ms_per_step': ms / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': 'LarvaNet x4 training step, batch 16 per GPU, 48x48 LR patches, L1 multi-exit loss, '
-                               'M=4 B=4,4,4,4, AdamW (BASELINE.json configs[1])',
-                   'global_batch': BATCH * world, 'parallelism': f'dp{world}',
-                   'l2': 'inputs rotate over 8 resident batches; saved activations+gradients (~330 MB/step) exceed the 126 MB L2'},
+        'config': headline_config(world),
         'e2e': {'value': e2e, 'unit': 'patches/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                 'ms_per_step': ms_e2e / a.steps},
         'gpu_launches': int(launches),
         'tflops_per_gpu': flops_train_per_patch() * BATCH / (ms / a.steps * 1e-3) / 1e12,
+        'long_run': {'steps': long_steps, 'value': BATCH * world * long_steps / (ms_long * 1e-3),
+                     'ms_per_step': ms_long / long_steps},
+        'dp_exchange': (None if world == 1 else
+                        'fused peer-memory all-reduce + AdamW + re-pack kernel (lv_dp_adamw_pack_step)' if eng._dp_fused()
+                        else 'symmetric-memory two-shot all-reduce' if eng._symm is not None else 'NCCL all-reduce'),
     }
 
     # ---- instrumented pass: CUDA events around every conv launch of one eager training step.  Every rank runs it
@@ -291,10 +380,10 @@ def run_ours(a):
         ach = float(fl.sum() / durs.sum() / 1e12)
         peak = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
         line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
-                            # dram__bytes_read.sum + dram__bytes_write.sum of the step's 80 chained layers from the
-                            # ncu --set full capture in profiles/r01c_conv_chain_ncu_full_summary.txt (two launches
-                            # there: 64 + 16 layers), per training step; algorithmic: 80 x 3.54 MB of saved activations
-                            'traffic': 320.1e6 / max(1, len(recs)),
+                            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, read from the
+                            # committed summary of the final build's `ncu --set full` capture (tools/ncu_summary.py
+                            # writes profiles/roofline_traffic.json); null when no capture of this build exists
+                            'traffic': roofline_traffic('conv3x3_chain_kernel'),
                             'kernel': 'conv3x3_chain_kernel<48,48> (forward + backward-data conv layers of the step, persistent data-flow launch)',
                             'launches_timed': len(recs), 'avg_launch_us': float(durs.mean() * 1e6),
                             'peak_source': peaks_src + ', sustained bf16 (kernel timed inside a long step)'}
@@ -359,6 +448,23 @@ def run_ours(a):
                          'value_l2_flushed: 192 MB write between frames'},
     }
 
+    # ---- the other BASELINE.json configurations, each with its own `config.workload`
+    del dev_pool, host_pool, feeder
+    eng._train.clear()
+    eng._infer.clear()
+    torch.cuda.empty_cache()
+    legs = {}
+    if world == 1:
+        legs['cfg3_edsr_1080p'] = leg_cfg3(dev, timed, engines, float(peaks['bf16_tflops']))
+    legs['cfg4_v2_global128'] = leg_cfg4(world, rank, dev, timed, engines)
+    legs['cfg5_256_frames'] = leg_cfg5(world, rank, dev, model, eng, barrier)
+    line['configs'] = legs
+    if rank == 0 and world == 1 and not a.no_gpu_baseline:
+        line['gpu_library_baseline'] = gpu_library_baseline(dev)
+        best = max(m['train_patches_per_s'] for m in line['gpu_library_baseline']['modes'].values())
+        besti = max(m['infer_720p_mpix_per_s'] for m in line['gpu_library_baseline']['modes'].values())
+        line['gpu_library_baseline']['ours_over_best_library'] = {'train': value / best,
+                                                                  'infer_720p': line['inference']['value'] / besti}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_sample()
     elif rank == 0:
@@ -368,6 +474,124 @@ def run_ours(a):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _plugin(kind, flags, training):
+    import importlib
+    m = importlib.import_module('models.' + kind).create_model()
+    m.parse_args(flags)
+    m.prepare(is_training=training, scales=[4])
+    return m
+
+
+def leg_cfg3(dev, timed, engines, peak_burst):
+    """BASELINE.json configs[2]: EDSR-baseline x4 (16 resblocks, 64 ch) inference, 480x270 -> 1920x1080."""
+    import torch
+    from larvanet_b200 import synth
+    m = _plugin('edsr', ['--edsr_conv_features=64', '--edsr_res_blocks=16', '--precision=bf16'], False)
+    m.get_model().load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_edsr_params(64, 16, 4, seed=0).items()})
+    eng = m.get_model().engine()
+    engines.append(eng)
+    frames = [torch.from_numpy(synth.make_images(1, 270, 480, seed=7 + i)[0]).to(dev) for i in range(2)]
+    steps = 20
+    ms = timed(lambda i: eng.forward(frames[i & 1]), steps, 4)
+    engines.remove(eng)
+    hr_px = 16 * 270 * 480
+    flops = 2.0 * 1983321 * 270 * 480          # SURVEY.md 8a row a10: 1,983,321 MAC per LR pixel
+    sec = ms * 1e-3 / steps
+    out = {'config': {'workload': 'EDSR-baseline x4 (16 resblocks, 64 ch) inference, batch 1, 480x270 -> 1920x1080 '
+                                  '(BASELINE.json configs[2])',
+                      'l2': 'back-to-back frames; 64-channel maps at 2x/4x resolution (66 / 265 MB) exceed the L2'},
+           'metric': 'sr_x4_output_mpix_per_s', 'unit': 'Mpix/s', 'value': hr_px / sec / 1e6, 'ms_per_frame': sec * 1e3,
+           'roofline': {'bound': 'tensor', 'achieved': flops / sec / 1e12, 'peak': peak_burst, 'unit': 'TFLOP/s',
+                        'frac': flops / sec / 1e12 / peak_burst, 'traffic': None,
+                        'kernel': 'whole network: row-marching chain (64->64 body) + conv3x3_tc (64->256 PixelShuffle, 64->3)'},
+           'row_path': bool(eng.use_row_path(1, 270, 480))}
+    del m, eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_cfg4(world, rank, dev, timed, engines):
+    """BASELINE.json configs[3]: LarvaNetV2 x4 data-parallel training, GLOBAL batch 128 of 64x64 patches (strong scaling:
+    128/N patches per GPU), gradient exchange as in the headline."""
+    import torch
+    from larvanet_b200 import dist as lvdist, synth
+    GB, P4 = 128, 64
+    m = _plugin('LarvaNetV2', ['--num_modules=4', '--num_blocks=4,4,4,4', '--precision=bf16'], True)
+    m.volume_per_step, m.global_step = P4 * P4 * GB * 3, 1
+    m.args.val_volume = 1e30
+    m.get_model().load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_larva_params(BLOCKS, v2=True, seed=0).items()})
+    eng = m._engine()
+    if world > 1:
+        eng.set_data_parallel(world)
+    engines.append(eng)
+    b, e = lvdist.shard_range(GB, rank, world)
+    pool = []
+    for i in range(2):
+        lr, hr = synth.make_images(e - b, P4, P4, seed=300 + 17 * rank + i)
+        pool.append((torch.from_numpy(lr).to(dev), torch.from_numpy(hr).to(dev)))
+
+    def step(i):
+        x, t = pool[i & 1]
+        loss = eng.train_step(x, t)
+        m.optim.step()
+        return loss
+
+    steps = 10
+    ms = timed(step, steps, 3)
+    engines.remove(eng)
+    sec = ms * 1e-3 / steps
+    flops = 2.0 * 2864160 * P4 * P4 * GB        # SURVEY.md 8a row a9: 2,864,160 MAC per LR pixel per step
+    out = {'config': {'workload': 'LarvaNetV2 x4 training step, GLOBAL batch 128 of 64x64 LR patches, M=4 B=4,4,4,4, L1 '
+                                  'multi-exit + tail loss, AdamW (BASELINE.json configs[3])',
+                      'global_batch': GB, 'per_gpu_batch': e - b, 'parallelism': f'dp{world}', 'scaling': 'strong'},
+           'metric': 'train_patches_per_s', 'unit': 'patches/s', 'value': GB / sec, 'ms_per_step': sec * 1e3,
+           'tflops_total': flops / sec / 1e12, 'row_path': bool(eng.use_row_path(e - b, P4, P4))}
+    del m, eng, pool
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_cfg5(world, rank, dev, model, eng, barrier):
+    """BASELINE.json configs[4]: 256 synthetic 480x270 frames sharded round-robin over the GPUs (dist.frames_for_rank),
+    no collective; sweep over the per-launch batch size."""
+    import torch
+    import torch.distributed as dist
+    from larvanet_b200 import dist as lvdist, synth
+    frames, H5, W5 = 256, 270, 480
+    mine = lvdist.frames_for_rank(frames, rank, world)
+    hr_px = 16 * H5 * W5
+    sweep = {}
+    for bs in (1, 8, 32):
+        if bs > len(mine):
+            continue
+        x = torch.from_numpy(synth.make_images(bs, H5, W5, seed=500 + rank)[0]).to(dev)
+        nb = len(mine) // bs
+        for _ in range(3):
+            eng.forward(x)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nb):
+            eng.forward(x)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        done = nb * bs * world
+        sweep[f'batch{bs}'] = {'mpix_per_s': done * hr_px / (float(ms.item()) * 1e-3) / 1e6, 'frames': done,
+                               'ms_total': float(ms.item()), 'row_path': bool(eng.use_row_path(bs, H5, W5))}
+        eng._infer.clear()
+        del x
+        torch.cuda.empty_cache()
+    best = max(sweep.values(), key=lambda v: v['mpix_per_s'])
+    return {'config': {'workload': 'LarvaNet x4 batch-sharded inference of 256 synthetic 480x270 frames -> 1920x1080, frames '
+                                   'dealt round-robin to the GPUs, no collective (BASELINE.json configs[4])',
+                       'frames_per_gpu': len(mine), 'parallelism': f'frames/{world}'},
+            'metric': 'sr_x4_output_mpix_per_s', 'unit': 'Mpix/s', 'value': best['mpix_per_s'], 'sweep': sweep,
+            'tflops_per_gpu': best['mpix_per_s'] * 1e6 / 16 * flops_infer_per_lr_px() / 1e12 / world}
 
 
 def steady_state_chain(dev, peak_burst):
@@ -414,6 +638,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--no-gpu-baseline', dest='no_gpu_baseline', action='store_true')
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

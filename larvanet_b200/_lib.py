@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'liblarvanet_b200.so')
+LIB_PATH = os.environ.get('LARVANET_B200_LIB') or os.path.join(HERE, 'liblarvanet_b200.so')   # env: A/B builds (developer)
 
 LV_F32, LV_BF16 = 0, 1
 LV_EPI_NHWC, LV_EPI_PS4_NCHW, LV_EPI_PS2_NHWC, LV_EPI_RGB_NCHW = 0, 1, 2, 3

@@ -35,15 +35,41 @@
 namespace lv {
 
 extern int g_use_pdl;
+extern long long* g_timeline;
 
 namespace row {
 
 constexpr int kMaxLayers = 96;   // LV_CHAIN_MAX_LAYERS
 constexpr int kLanes = 128, kRowPx = kLanes + 2;
+// Warp roles (416 threads): 0-7 epilogue (two groups), 8 MMA issuer, 9 scheduler, 10-11 row producers, 12 publisher.
+// Why a scheduler warp: the tensor pipe's instruction queue holds only ~4 MMAs (~270 clk of work), and ONE thread that
+// waits for the accumulator block and the input row, computes the row's descriptors, issues and commits spends ~1,100 clk
+// per row outside the issue loop (measured: 2,330 clk per row for 680 clk of MMAs, tensor pipe 29 % busy; the 16x8-tile
+// kernels pay the same ~1,000 clk per tile).  So everything but the issue itself moves to a second thread: the scheduler
+// waits, computes, and hands the issuer a ready-made command (descriptors, accumulate flags, barriers to commit to)
+// through a 4-deep shared-memory ring; the issuer's gap between two rows is one mbarrier wait + two 16-byte loads.
 constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 64;
-constexpr int kMmaWarp = kEpiWarps;
-constexpr int kPubWarp = kMmaWarp + 1 + kProdThreads / 32;
-constexpr int kThreads = kEpiThreads + 32 + kProdThreads + 32;   // 384
+constexpr int kMmaWarp = kEpiWarps;                       // 8
+constexpr int kSchedWarp = kMmaWarp + 1;                  // 9
+constexpr int kProdWarp0 = kSchedWarp + 1;                // 10, 11
+constexpr int kPubWarp = kProdWarp0 + kProdThreads / 32;  // 12
+constexpr int kThreads = (kPubWarp + 1) * 32;             // 416
+constexpr int kCmdSlots = 4;
+
+// one row of MMA work, written by the scheduler thread, read by the issuer thread (64 bytes)
+struct __align__(16) RowCmd {
+  uint32_t a_lo, b_lo;                 // low words of the A / B shared-memory descriptors (start address fields)
+  uint32_t ra_d, ra_b, ra_i, fa_i;     // run A: TMEM address, weight-row offset, idesc; idesc of its first-MMA form
+  uint32_t fc_d, fc_b, fc_i;           // tail of run A for the first MMA (when target 0 is cut off), fc_i == 0: none
+  uint32_t rb_d, rb_b, rb_i;           // run B (ring wrap), rb_i == 0: none
+  uint32_t acc;                        // bit 0: first MMA of run A accumulates, bit 1: first MMA of run B accumulates
+  uint32_t bars;                       // barrier INDICES (8 bits each; +1, 0 = none, for all but the first):
+                                       //   [0:8) row buffer free, [8:16) / [16:24) accumulator complete (output row yi-1 /
+                                       //   row yi on the image's bottom row), [24:32) weight buffer free (layer's last row)
+  uint32_t pad0, pad1;
+};
+static_assert(sizeof(RowCmd) == 64, "RowCmd is four 16-byte shared-memory loads");
+constexpr uint32_t kCmdStop = 0xffffffffu;   // a_lo of the terminating command
 
 struct Params {
   lv_conv_args layer[kMaxLayers];
@@ -52,8 +78,18 @@ struct Params {
 struct Geom {
   int N, H, W, P;           // P = W + 1: pitch of one image on the line
   int nstrips, rows_per_job, nblocks, total_jobs;
+  long long* stats;         // debug (lv_debug_set_timeline): per-role cycle counters of CTA 0, nullptr in production
 };
 
+// debug counters (CTA 0 only): [role * 8 + i]; role 0 = MMA thread, 1 = producer thread 0, 2 = epilogue warp 0 lane 0,
+// 3 = epilogue warp 4 lane 0
+__device__ __forceinline__ void stat_add(const Geom& g, int slot, long long v) {
+  if (g.stats != nullptr && blockIdx.x == 0) g.stats[slot] += v;
+}
+__device__ __forceinline__ long long stat_clk(const Geom& g) { return g.stats != nullptr ? clock64() : 0; }
+
+// Shared-memory budget: stay below the 196 KB carve-out step so that the SM keeps ~32 KB of L1 (kernel parameters,
+// bias vectors, whatever the epilogue spills): with the 228 KB step nothing is left and every such access goes to L2.
 template <int CIN, int NT, int NSTAGE, int WBUFS>
 struct Cfg {
   static constexpr int CH = CIN / 8;
@@ -67,9 +103,10 @@ struct Cfg {
   static constexpr int RING = (512 / NT) & ~1;       // accumulator blocks (even: block parity == epilogue group)
   static constexpr int TMEM_COLS = 512;
   static constexpr int PIECES = (kRowPx * CH + kProdThreads - 1) / kProdThreads;
-  static constexpr int NBARS = 2 * NSTAGE + 2 * RING + 2 * WBUFS + 4;
+  static constexpr int NBARS = 2 * NSTAGE + 2 * RING + 2 * WBUFS + 4 + 2 * kCmdSlots;
   static constexpr size_t smem_bytes() {
-    return static_cast<size_t>(WBUFS) * W_LAYER + static_cast<size_t>(NSTAGE) * A_STAGE + NBARS * 8 + 64;
+    return static_cast<size_t>(WBUFS) * W_LAYER + static_cast<size_t>(NSTAGE) * A_STAGE + kCmdSlots * sizeof(RowCmd) +
+           NBARS * 8 + 64;
   }
 };
 
@@ -97,6 +134,15 @@ __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t need) {
   (void)ld_acquire_gpu(p);
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& t) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 t;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(addr) : "memory");
+  return t;
+}
+
 // runtime-N instruction descriptor (M = 128, bf16 x bf16 -> fp32, both operands K-major)
 __device__ __forceinline__ uint32_t idesc_n(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
@@ -117,6 +163,105 @@ struct EpiCtx {
 
 constexpr int kKindPs4 = 100, kKindGeneric = -1;
 
+// Planar epilogue of one output row for one thread (one pixel x NT channels), straight-line for a compile-time flag set
+// EPI (bit0 ReLU, bit1 ReLU-mask, bit2 res1, bit3 res2).  Same arithmetic as chain::fast_tile, but the accumulator is read
+// and processed in two halves of NT/2 channels and the bias arrives by warp shuffle: ~100 live registers instead of ~170,
+// so the 416-thread CTA (128 registers per thread) does not spill in its hot loop.  All operand loads of the row are issued
+// before the accumulator wait (their latency hides behind the MMAs).
+template <int EPI, int NT>
+__device__ __forceinline__ void row_tile(const chain::FastEpi& e, float bias_a, float bias_b, bool valid, size_t o0,
+                                         size_t chunk_stride, uint32_t taddr, uint32_t tfull, uint32_t tempty, uint32_t parity,
+                                         long long* dbg = nullptr) {
+  long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;
+  if (dbg != nullptr) d0 = clock64();
+  constexpr int NCH = NT / 8, HC = NCH / 2, HALF = NT / 2;
+  constexpr bool do_relu = (EPI & 1) != 0, do_mask = (EPI & 2) != 0, do_res1 = (EPI & 4) != 0, do_res2 = (EPI & 8) != 0;
+  uint4 qm[do_mask ? NCH : 1], q1[do_res1 ? NCH : 1], q2[do_res2 ? NCH : 1];
+  if (valid) {
+    if constexpr (do_mask) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) qm[j] = chain::ldcg16(e.mask + o0 + j * chunk_stride);
+    }
+    if constexpr (do_res1) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) q1[j] = chain::ldcg16(e.res1 + o0 + j * chunk_stride);
+    }
+    if constexpr (do_res2) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) q2[j] = chain::ldcg16(e.res2 + o0 + j * chunk_stride);
+    }
+  }
+  if (dbg != nullptr) d1 = clock64();
+  mbar_wait_relaxed(tfull, parity);
+  tc_fence_after_sync();
+  if (dbg != nullptr) d2 = clock64();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v[HALF];
+    if constexpr (HALF == 24) {
+      tmem_ld16(taddr + h * HALF, v);
+      tmem_ld8(taddr + h * HALF + 16, v + 16);
+    } else {
+#pragma unroll
+      for (int j = 0; j < HALF / 16; ++j) tmem_ld16(taddr + h * HALF + j * 16, v + j * 16);
+    }
+    tmem_ld_wait();
+    if (dbg != nullptr) { if (h == 0) d3 = clock64(); else d4 += clock64(); }
+    if (h == 1) {
+      tc_fence_before_sync();
+      mbar_arrive(tempty);   // accumulator block free: the MMAs of a later row may overwrite it
+    }
+    if (dbg != nullptr && h == 1) d4 -= 0;
+    {
+      __nv_bfloat16* po = e.out + o0;
+#pragma unroll
+      for (int jj = 0; jj < HC; ++jj) {
+        const int j = h * HC + jj;
+        float* vj = v + 8 * jj;
+        // bias: lane l of every warp keeps bias[l] and bias[32 + l] in two registers and the values travel by warp
+        // shuffle -- any load here (L1 or shared memory) would queue behind the MMAs' operand reads (~300 clk each)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = 8 * j + i;
+          vj[i] += __shfl_sync(0xffffffffu, c < 32 ? bias_a : bias_b, c & 31);
+        }
+        if constexpr (do_relu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) vj[i] = fmaxf(vj[i], 0.f);
+        }
+        if constexpr (do_mask) {
+          const uint32_t w4[4] = {qm[j].x, qm[j].y, qm[j].z, qm[j].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            vj[2 * t] = (bf16_lo(w4[t]) > 0.f) ? vj[2 * t] : 0.f;
+            vj[2 * t + 1] = (bf16_hi(w4[t]) > 0.f) ? vj[2 * t + 1] : 0.f;
+          }
+        }
+        if constexpr (do_res1) {
+          const uint32_t w4[4] = {q1[j].x, q1[j].y, q1[j].z, q1[j].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { vj[2 * t] += bf16_lo(w4[t]); vj[2 * t + 1] += bf16_hi(w4[t]); }
+        }
+        if constexpr (do_res2) {
+          const uint32_t w4[4] = {q2[j].x, q2[j].y, q2[j].z, q2[j].w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { vj[2 * t] += bf16_lo(w4[t]); vj[2 * t + 1] += bf16_hi(w4[t]); }
+        }
+        if (valid) store8(po + j * chunk_stride, vj);
+      }
+    }
+    if (dbg != nullptr && h == 0) d4 = -clock64() + 0;   // start of the second half: d4 becomes (t_ld1_done - t_half0_done)
+  }
+  if (dbg != nullptr) {
+    const long long d5 = clock64();
+    dbg[0] += d1 - d0;        // operand loads issued
+    dbg[1] += d2 - d1;        // (second) accumulator wait: ~0 in stats mode
+    dbg[2] += d3 - d2;        // first TMEM load + wait
+    dbg[3] += d4;             // second TMEM load + wait (from the end of the first half's stores)
+    dbg[4] += d5 - d0;        // whole tile function
+  }
+}
+
 // All jobs of one layer for one epilogue thread (one line position = one pixel column of the strip).
 template <int KIND, int NT, int RING>
 __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_args& a, int l, int first, uint32_t k) {
@@ -130,17 +275,12 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
   fe.res_scale = a.res_scale;
   fe.relu = a.relu;
   float loss = 0.f;
-  constexpr bool kBiasRegs = (NT <= 48) && (KIND == 0 || KIND == 1 || KIND == 2 || KIND == 4);
-  float breg[kBiasRegs ? NT : 1];
+  long long st_wait = 0, st_drain = 0, st_rows = 0;   // debug counters (registers; flushed once per layer)
+  long long dbgv[5] = {0, 0, 0, 0, 0};
   const float* bias_g = a.bias;
-  if constexpr (kBiasRegs) {
-#pragma unroll
-    for (int i = 0; i < NT / 4; ++i) {
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + i);
-      breg[4 * i] = b4.x; breg[4 * i + 1] = b4.y; breg[4 * i + 2] = b4.z; breg[4 * i + 3] = b4.w;
-    }
-  }
+  // this lane's two bias values for row_tile's shuffle broadcast (channels lane and 32 + lane)
+  const float bias_a = (a.bias != nullptr && cx.lane < NT) ? __ldg(a.bias + cx.lane) : 0.f;
+  const float bias_b = (a.bias != nullptr && 32 + cx.lane < NT) ? __ldg(a.bias + 32 + cx.lane) : 0.f;
   for (int job = first; job < cx.g.total_jobs; job += cx.G) {
     const int bk = job / cx.g.nstrips, u = job - bk * cx.g.nstrips;
     const int y0 = bk * cx.g.rows_per_job;
@@ -163,6 +303,13 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
       const uint32_t tfull = cx.tfull0 + 8u * blk, tempty = cx.tempty0 + 8u * blk;
       const size_t o0 = o_img + static_cast<size_t>(yo) * cx.row_stride;
       const uint32_t seen = (cx.nlayers > 1) ? *cx.pub_seen : 0u;
+      const bool st = cx.g.stats != nullptr && cx.lane == 0 && (cx.m == 0);
+      long long c0 = 0, c1 = 0;
+      if (cx.g.stats != nullptr) {       // debug only: separate "waiting for the accumulator" from "draining it"
+        c0 = clock64();
+        mbar_wait_relaxed(tfull, par);
+        c1 = clock64();
+      }
       if constexpr (KIND == kKindPs4) {
         loss += chain::ps4_tile<NT>(a, bias_g, valid, n, yo, x, cx.g.H, cx.g.W, o0, cx.chunk_stride, taddr, tfull, tempty, par);
       } else if constexpr (KIND == kKindGeneric) {
@@ -178,7 +325,12 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
         tc_fence_before_sync();
         mbar_arrive(tempty);
       } else {
-        chain::fast_tile<KIND, NT, kBiasRegs>(fe, breg, bias_g, valid, o0, cx.chunk_stride, taddr, tfull, tempty, par);
+        row_tile<KIND, NT>(fe, bias_a, bias_b, valid, o0, cx.chunk_stride, taddr, tfull, tempty, par, st ? dbgv : nullptr);
+      }
+      if (st) {
+        st_wait += c1 - c0;
+        st_drain += clock64() - c1;
+        st_rows += 1;
       }
       if (cx.nlayers > 1) {
         // this warp's quarter of the row is on its way to global memory: hand it to the publisher warp (ring of 4 rows)
@@ -200,9 +352,18 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
     loss = warp_sum(loss);
     if (cx.lane == 0) atomicAdd(a.loss_sum, static_cast<double>(loss));
   }
+  if (cx.g.stats != nullptr && cx.lane == 0 && cx.m == 0) {
+    const int base = 16 + 8 * cx.eg;
+    stat_add(cx.g, base + 0, st_wait);
+    stat_add(cx.g, base + 1, st_drain);
+    stat_add(cx.g, base + 2, st_rows);
+    if (cx.eg == 0) for (int i = 0; i < 5; ++i) stat_add(cx.g, 32 + i, dbgv[i]);
+  }
   return k;
 }
 
+// 13 warps: the register file is split per scheduler (16 K registers each) and one scheduler holds 4 of the 13 warps, so
+// the budget is 128 registers per thread; the hot epilogues (row_tile) are written to stay below it
 template <int CIN, int NT, int NSTAGE, int WBUFS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Geom g, uint32_t* __restrict__ done, const int rot) {
@@ -214,7 +375,8 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
 
   uint8_t* sW = smem;
   uint8_t* sA = sW + WBUFS * C_::W_LAYER;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + NSTAGE * C_::A_STAGE);
+  RowCmd* cmds = reinterpret_cast<RowCmd*>(sA + NSTAGE * C_::A_STAGE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cmds + kCmdSlots);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
@@ -223,6 +385,11 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
   auto wfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + b); };
   auto wfree_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + WBUFS + b); };
   auto pub_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + s); };
+  auto empty_idx = [&](int s) { return static_cast<uint32_t>(NSTAGE + s); };
+  auto tfull_idx = [&](uint32_t b) { return static_cast<uint32_t>(2 * NSTAGE) + b; };
+  auto wfree_idx = [&](int b) { return static_cast<uint32_t>(2 * NSTAGE + 2 * RING + WBUFS + b); };
+  auto cmd_full_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + 4 + s); };
+  auto cmd_free_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + 4 + kCmdSlots + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C_::NBARS);
   uint32_t* s_last = tmem_slot + 1;
   volatile uint32_t* pub_seen = tmem_slot + 2;   // rows whose completion the publisher warp has observed
@@ -241,6 +408,10 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
       mbar_init(wfree_bar(b), 1);
     }
     for (int s = 0; s < 4; ++s) mbar_init(pub_bar(s), kEpiWarps / 2);
+    for (int s = 0; s < kCmdSlots; ++s) {
+      mbar_init(cmd_full_bar(s), 1);
+      mbar_init(cmd_free_bar(s), 1);
+    }
     tmem_slot[2] = 0u;
     mbar_fence_init();
   }
@@ -282,12 +453,13 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
       }
     }
     __syncwarp();
-  } else if (warp > kMmaWarp) {
+  } else if (warp >= kProdWarp0) {
     // =============================== producers: dependency wait + input rows -> smem ===============================
-    const int ptid = threadIdx.x - (kEpiThreads + 32);
+    const int ptid = threadIdx.x - kProdWarp0 * 32;
     const int ddy = lane / 3 - 1, ddx = lane % 3 - 1;   // lanes 0..8 watch the 3x3 job neighbourhood
     const size_t row_stride = static_cast<size_t>(C_::CH) * g.W * 8;   // elements between image rows
     uint32_t fill = 0;
+    long long sp_flag = 0, sp_empty = 0, sp_issue = 0, sp_rows = 0;   // debug counters (registers)
     pdl_wait();
     for (int l = 0; l < nlayers; ++l) {
       const __nv_bfloat16* src_base = reinterpret_cast<const __nv_bfloat16*>(P.layer[l].src[0]);
@@ -307,6 +479,7 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
           }
           pc_off[i] = off;
         }
+        const long long pc0 = stat_clk(g);
         if (l > 0) {
           if (lane < 9) {
             const int bk = job / g.nstrips;
@@ -316,10 +489,13 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
           }
           __syncwarp();
         }
+        sp_flag += stat_clk(g) - pc0;      // dependency (flag) wait
         const int ya = max(j.y0 - 1, 0), yb = min(j.y1 + 1, g.H);
         for (int yi = ya; yi < yb; ++yi, ++fill) {
           const int stage = fill % NSTAGE;
+          const long long pc1 = stat_clk(g);
           mbar_wait_relaxed(empty_bar(stage), ((fill / NSTAGE) & 1) ^ 1);
+          const long long pc2 = stat_clk(g);
           const __nv_bfloat16* src = src_base + static_cast<size_t>(yi) * row_stride;
           const uint32_t dst0 = smem_u32(sA + stage * C_::A_STAGE) + ptid * 16;
 #pragma unroll
@@ -330,13 +506,19 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
             }
           }
           cp_async_mbar_arrive_noinc(full_bar(stage));
+          sp_empty += pc2 - pc1;                 // waiting for a free row buffer
+          sp_issue += stat_clk(g) - pc2;         // issuing the copies
+          sp_rows += 1;
         }
       }
     }
     cp_async_wait<0>();
-  } else if (warp == kMmaWarp) {
-    // =============================== MMA issuer (one elected lane) ================================
-    if (elect_one()) {
+    if (ptid == 0) {
+      stat_add(g, 8, sp_flag); stat_add(g, 9, sp_empty); stat_add(g, 10, sp_issue); stat_add(g, 11, sp_rows);
+    }
+  } else if (warp == kSchedWarp) {
+    // =============================== scheduler: waits + descriptors -> command ring ================================
+    if (lane == 0) {
       auto load_weights = [&](int l) {
         const int b = l % WBUFS;
         mbar_arrive_expect_tx(wfull_bar(b), C_::W_LAYER);
@@ -346,7 +528,8 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
                        C_::W_PLANE, wfull_bar(b));
       };
       load_weights(0);   // packed weights are never written while a launch chain is in flight: no pdl_wait needed
-      uint32_t fill = 0, k = 0;
+      uint32_t fill = 0, k = 0, ncmd = 0;
+      long long ss_setup = 0, ss_tempty = 0, ss_full = 0, ss_slot = 0, ss_rows = 0;   // debug counters (registers)
       uint32_t free_pending = 0, free_phase = 0;   // bit b: MMAs reading weight buffer b outstanding / wfree parity
       for (int l = 0; l < nlayers; ++l) {
         const int wb = l % WBUFS;
@@ -360,12 +543,15 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
           load_weights(l + 1);
         }
         mbar_wait(wfull_bar(wb), (l / WBUFS) & 1);
-        const uint32_t sW_addr = smem_u32(sW + wb * C_::W_LAYER);
-        bool any = false;
+        const uint32_t b_lo = static_cast<uint32_t>(umma_smem_desc(smem_u32(sW + wb * C_::W_LAYER), C_::W_PLANE, 128));
+        // the layer's last row of this CTA also commits the "weight buffer free" barrier: find it first
+        int last_job = -1;
+        for (int job = first_job(l); job < g.total_jobs; job += G) last_job = job;
         for (int job = first_job(l); job < g.total_jobs; job += G) {
           const Job j = decode(job);
           const int ya = max(j.y0 - 1, 0), yb = min(j.y1 + 1, g.H);
-          for (int yi = ya; yi < yb; ++yi, ++fill) {
+          for (int yi = ya; yi < yb; ++yi, ++fill, ++ncmd) {
+            const long long c0 = stat_clk(g);
             // targets t = 0,1,2: output row yi+1-t through vertical tap ky = t (weight rows [t*NT, (t+1)*NT));
             // the valid ones form an interval [ta, tb]
             int ta = 3, tb = -1;
@@ -378,79 +564,114 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
             // so the blocks of targets t, t+1 are adjacent (ascending) unless kk_t % RING == 0 (the ring wraps there)
             const uint32_t kk0 = k + static_cast<uint32_t>(yi + 1 - j.y0);      // target 0 (may be "virtual" when invalid)
             auto col_of = [&](int t) { return (RING - 1 - ((kk0 - static_cast<uint32_t>(t)) % RING)) * NT; };
-            // Runs = maximal groups of valid targets issued as ONE MMA (adjacent blocks, N = NT * targets).  `rr`: every
-            // MMA but the row's first; `fr`: the first (kx = 0, k-step 0), which must additionally separate blocks it
-            // OVERWRITES (first contribution to that output row: target 0 always, target 1 on the image's top row)
-            // from blocks it accumulates into -- the flag is per instruction.
-            uint32_t rr_d[2], rr_b[2], rr_i[2], fr_d[3], fr_b[3], fr_i[3], fr_acc[3];
-            int nr = 0, nf = 0;
-            if (ta <= tb) {
-              int ts = ta;
-              while (ts <= tb) {
-                int te = ts;
-                while (te < tb && ((kk0 - static_cast<uint32_t>(te)) % RING) != 0) ++te;
-                rr_d[nr] = tmem_base + col_of(ts);
-                rr_b[nr] = static_cast<uint32_t>(ts * NT);          // weight row offset (16 B per row)
-                rr_i[nr] = idesc_n((te - ts + 1) * NT);
-                ++nr;
-                // the same run for the first MMA, cut after target 0 when the rest accumulates
-                int fs = ts;
-                if (yi > 0 && ts == 0 && te > 0) {
-                  fr_d[nf] = tmem_base + col_of(0); fr_b[nf] = 0; fr_i[nf] = idesc_n(NT); fr_acc[nf] = 0u; ++nf;
-                  fs = 1;
-                }
-                fr_d[nf] = tmem_base + col_of(fs);
-                fr_b[nf] = static_cast<uint32_t>(fs * NT);
-                fr_i[nf] = idesc_n((te - fs + 1) * NT);
-                fr_acc[nf] = (yi == 0 || fs == 0) ? 0u : 1u;
-                ++nf;
-                ts = te + 1;
-              }
-              // blocks overwritten by this row must have been drained by the epilogue (their previous output row)
-              if (ta == 0) {
-                mbar_wait(tempty_bar(kk0 % RING), ((kk0 / RING) & 1u) ^ 1u);
-              }
-              if (yi == 0 && tb >= 1) {
-                const uint32_t kk1 = kk0 - 1u;
-                mbar_wait(tempty_bar(kk1 % RING), ((kk1 / RING) & 1u) ^ 1u);
-              }
-            }
+            // Runs = maximal groups of valid targets issued as ONE MMA (adjacent blocks, N = NT * targets): A = [ta..ea],
+            // B = [ea+1..tb] (only when the ring wraps inside the interval).  The row's first MMA (kx = 0, k-step 0)
+            // must additionally separate blocks it OVERWRITES (first contribution to that output row: target 0 always,
+            // target 1 on the image's top row) from blocks it accumulates into -- the flag is per instruction -- so
+            // run A is cut after target 0 when the rest accumulates.
+            int ea = ta;
+            while (ea < tb && ((kk0 - static_cast<uint32_t>(ea)) % RING) != 0) ++ea;
+            const bool has_b = ea < tb;
+            const bool cut = yi > 0 && ta == 0 && ea > 0;
             const int stage = fill % NSTAGE;
-            mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
-            fence_proxy_async_smem();
-            tc_fence_after_sync();
-            if (nr > 0) {
-              const uint64_t adesc0 = umma_smem_desc(smem_u32(sA + stage * C_::A_STAGE), C_::A_PLANE, 128);
-              const uint64_t bdesc0 = umma_smem_desc(sW_addr, C_::W_PLANE, 128);
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-#pragma unroll
-                for (int ks = 0; ks < C_::KSTEPS; ++ks) {
-                  // descriptor start addresses move in 16-byte units: horizontal tap = one pixel, k-step = two chunk planes
-                  const uint64_t adesc = adesc0 + static_cast<uint64_t>((kx * 16 + 2 * ks * C_::A_PLANE) >> 4);
-                  const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((kx * C_::W_KX + 2 * ks * C_::W_PLANE) >> 4);
-                  if (kx == 0 && ks == 0) {
-                    for (int i = 0; i < nf; ++i) umma_bf16(fr_d[i], adesc, bdesc + fr_b[i], fr_i[i], fr_acc[i]);
-                  } else {
-                    umma_bf16(rr_d[0], adesc, bdesc + rr_b[0], rr_i[0], 1u);
-                    if (nr > 1) umma_bf16(rr_d[1], adesc, bdesc + rr_b[1], rr_i[1], 1u);
-                  }
-                }
-              }
+            const uint32_t ra_i = idesc_n((ea - ta + 1) * NT);
+            const uint32_t tfa = (yi - 1 >= j.y0 && yi - 1 < j.y1) ? 1u + tfull_idx((k + static_cast<uint32_t>(yi - 1 - j.y0)) % RING) : 0u;
+            const uint32_t tfb = (yi == g.H - 1 && yi >= j.y0 && yi < j.y1) ? 1u + tfull_idx((k + static_cast<uint32_t>(yi - j.y0)) % RING) : 0u;
+            const uint32_t wfr = (job == last_job && yi == yb - 1) ? 1u + wfree_idx(wb) : 0u;
+            const uint4 q0 = make_uint4(static_cast<uint32_t>(umma_smem_desc(smem_u32(sA + stage * C_::A_STAGE), C_::A_PLANE, 128)),
+                                        b_lo, tmem_base + col_of(ta), static_cast<uint32_t>(ta * NT));
+            const uint4 q1 = make_uint4(ra_i, cut ? idesc_n(NT) : ra_i, tmem_base + col_of(1), static_cast<uint32_t>(NT));
+            const uint4 q2 = make_uint4(cut ? idesc_n(ea * NT) : 0u, tmem_base + col_of(ea + 1), static_cast<uint32_t>((ea + 1) * NT),
+                                        has_b ? idesc_n((tb - ea) * NT) : 0u);
+            const uint4 q3 = make_uint4(((yi == 0 || ta == 0) ? 0u : 1u) | ((yi == 0) ? 0u : 2u),
+                                        empty_idx(stage) | (tfa << 8) | (tfb << 16) | (wfr << 24), 0u, 0u);
+            const long long c1 = stat_clk(g);
+            // blocks overwritten by this row must have been drained by the epilogue (their previous output row)
+            if (ta == 0) mbar_wait(tempty_bar(kk0 % RING), ((kk0 / RING) & 1u) ^ 1u);
+            if (yi == 0 && tb >= 1) {
+              const uint32_t kk1 = kk0 - 1u;
+              mbar_wait(tempty_bar(kk1 % RING), ((kk1 / RING) & 1u) ^ 1u);
             }
-            umma_commit(empty_bar(stage));   // row buffer reusable once these MMAs retire
-            // output rows this input row completes: yi-1 always, yi too on the image's bottom row
-            if (yi - 1 >= j.y0 && yi - 1 < j.y1) umma_commit(tfull_bar((k + static_cast<uint32_t>(yi - 1 - j.y0)) % RING));
-            if (yi == g.H - 1 && yi >= j.y0 && yi < j.y1) umma_commit(tfull_bar((k + static_cast<uint32_t>(yi - j.y0)) % RING));
-            any = true;
+            const long long c2 = stat_clk(g);
+            mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
+            const long long c3 = stat_clk(g);
+            const uint32_t slot = ncmd % kCmdSlots;
+            mbar_wait(cmd_free_bar(slot), ((ncmd / kCmdSlots) & 1u) ^ 1u);
+            uint4* dst = reinterpret_cast<uint4*>(&cmds[slot]);
+            st_shared_v4(smem_u32(dst), q0);
+            st_shared_v4(smem_u32(dst + 1), q1);
+            st_shared_v4(smem_u32(dst + 2), q2);
+            st_shared_v4(smem_u32(dst + 3), q3);
+            mbar_arrive(cmd_full_bar(slot));   // release: the command (and the barrier completions observed above)
+            if (g.stats != nullptr) {
+              ss_setup += c1 - c0; ss_tempty += c2 - c1; ss_full += c3 - c2; ss_slot += clock64() - c3; ss_rows += 1;
+            }
           }
           k += static_cast<uint32_t>(j.y1 - j.y0);
         }
-        if (any) {
-          umma_commit(wfree_bar(wb));
-          free_pending |= 1u << wb;
-        }
+        if (last_job >= 0) free_pending |= 1u << wb;
       }
+      // terminating command
+      {
+        const uint32_t slot = ncmd % kCmdSlots;
+        mbar_wait(cmd_free_bar(slot), ((ncmd / kCmdSlots) & 1u) ^ 1u);
+        st_shared_v4(smem_u32(&cmds[slot]), make_uint4(kCmdStop, 0u, 0u, 0u));
+        mbar_arrive(cmd_full_bar(slot));
+      }
+      stat_add(g, 0, ss_setup); stat_add(g, 4, ss_tempty); stat_add(g, 1, ss_full); stat_add(g, 5, ss_slot);
+      stat_add(g, 3, ss_rows);
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // =============================== MMA issuer (one elected lane): executes the command ring =======================
+    if (elect_one()) {
+      long long si_wait = 0, si_issue = 0, si_commit = 0;   // debug counters (registers)
+      // high word of both operand descriptors: SBO = 128 B (8 rows x 16 B core matrices), descriptor version 1; the low
+      // word (start address + LBO) comes with the command
+      constexpr uint64_t kDescHi = (static_cast<uint64_t>((128 >> 4) & 0x3fff) << 32) | (static_cast<uint64_t>(1) << 46);
+      for (uint32_t n = 0;; ++n) {
+        const uint32_t slot = n % kCmdSlots;
+        const long long c0 = stat_clk(g);
+        mbar_wait(cmd_full_bar(slot), (n / kCmdSlots) & 1u);
+        const uint32_t ca = smem_u32(&cmds[slot]);
+        const uint4 w0 = ld_shared_v4(ca);
+        if (w0.x == kCmdStop) break;
+        const uint4 w1 = ld_shared_v4(ca + 16), w2 = ld_shared_v4(ca + 32), w3 = ld_shared_v4(ca + 48);
+        mbar_arrive(cmd_free_bar(slot));
+        fence_proxy_async_smem();   // cp.async (generic proxy) writes of the row -> UMMA (async proxy) reads
+        tc_fence_after_sync();
+        const long long c1 = stat_clk(g);
+        // RowCmd fields: w0 = {a_lo, b_lo, ra_d, ra_b}, w1 = {ra_i, fa_i, fc_d, fc_b}, w2 = {fc_i, rb_d, rb_b, rb_i},
+        // w3 = {acc, empty_bar, tfull_a, tfull_b}
+        const uint64_t adesc0 = kDescHi | w0.x;
+        const uint64_t bdesc0 = kDescHi | w0.y;
+        const bool cut = w2.x != 0u, has_b = w2.w != 0u;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int ks = 0; ks < C_::KSTEPS; ++ks) {
+            // descriptor start addresses move in 16-byte units: horizontal tap = one pixel, k-step = two chunk planes
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>((kx * 16 + 2 * ks * C_::A_PLANE) >> 4);
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((kx * C_::W_KX + 2 * ks * C_::W_PLANE) >> 4);
+            if (kx == 0 && ks == 0) {
+              umma_bf16(w0.z, adesc, bdesc + w0.w, w1.y, w3.x & 1u);
+              if (cut) umma_bf16(w1.z, adesc, bdesc + w1.w, w2.x, 1u);
+              if (has_b) umma_bf16(w2.y, adesc, bdesc + w2.z, w2.w, (w3.x >> 1) & 1u);
+            } else {
+              umma_bf16(w0.z, adesc, bdesc + w0.w, w1.x, 1u);
+              if (has_b) umma_bf16(w2.y, adesc, bdesc + w2.z, w2.w, 1u);
+            }
+          }
+        }
+        const long long c2 = stat_clk(g);
+        const uint32_t bi = w3.y;
+        umma_commit(bar0 + 8u * (bi & 0xffu));                                         // row buffer reusable once these MMAs retire
+        if ((bi >> 8) & 0xffu) umma_commit(bar0 + 8u * (((bi >> 8) & 0xffu) - 1u));    // output row yi-1 complete
+        if ((bi >> 16) & 0xffu) umma_commit(bar0 + 8u * (((bi >> 16) & 0xffu) - 1u));  // image's bottom row: row yi complete
+        if (bi >> 24) umma_commit(bar0 + 8u * ((bi >> 24) - 1u));                      // layer's last row: weight buffer free
+        if (g.stats != nullptr) { si_wait += c1 - c0; si_issue += c2 - c1; si_commit += clock64() - c2; }
+      }
+      stat_add(g, 2, si_issue); stat_add(g, 6, si_commit); stat_add(g, 7, si_wait);
     }
     __syncwarp();
   } else {
@@ -525,6 +746,7 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
 // small problems, long jobs amortise the two halo rows on large ones
 static Geom make_geom(int n, int h, int w, int ctas) {
   Geom g;
+  g.stats = nullptr;
   g.N = n; g.H = h; g.W = w; g.P = w + 1;
   const long long line = static_cast<long long>(n) * g.P - 1;
   g.nstrips = static_cast<int>((line + kLanes - 1) / kLanes);
@@ -555,8 +777,7 @@ long long conv3x3_row_workspace_bytes(int n, int h, int w) {
 // checks the persistent grid can be co-resident (the data-flow waits need every CTA running) and opts into the
 // dynamic shared memory, once per device
 template <typename K>
-static int prepare_kernel(K kern, size_t smem, int threads, int grid, bool needs_coresidency) {
-  static size_t configured[64] = {0};
+static int prepare_kernel(K kern, size_t smem, int threads, int grid, bool needs_coresidency, size_t (&configured)[64]) {
   int dev = 0;
   LV_CUDA_OK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) dev = 0;
@@ -585,6 +806,7 @@ static int launch_row(const lv_conv_args* layers, int count, void* sync_ws, long
   int ctas = max_ctas > 0 ? max_ctas : sm_count();
   if (ctas > sm_count()) ctas = sm_count();
   row::Geom g = row::make_geom(a0.n, a0.h, a0.w, ctas);
+  g.stats = g_timeline;
   if (g.total_jobs < ctas) ctas = g.total_jobs;
   if (count > 1) {
     LV_CHECK_ARG(sync_ws != nullptr && sync_ws_bytes >= (static_cast<long long>(g.total_jobs) + 1) * 4,
@@ -592,7 +814,8 @@ static int launch_row(const lv_conv_args* layers, int count, void* sync_ws, long
                  (static_cast<long long>(g.total_jobs) + 1) * 4);
   }
   auto kern = row::conv3x3_row_kernel<CIN, NT, NSTAGE, WBUFS>;
-  int rc = prepare_kernel(kern, C_::smem_bytes(), row::kThreads, ctas, count > 1);
+  static size_t configured[64] = {0};   // per kernel instantiation (this function is one) and per device
+  int rc = prepare_kernel(kern, C_::smem_bytes(), row::kThreads, ctas, count > 1, configured);
   if (rc != LV_OK) return rc;
   static thread_local row::Params params;   // staging only; the launch copies it by value
   for (int i = 0; i < count; ++i) params.layer[i] = layers[i];
@@ -631,8 +854,8 @@ int conv3x3_row_chain(const lv_conv_args* layers, int count, void* sync_ws, long
   }
   if (static_cast<long long>(a0.n) * a0.h * a0.w == 0) return LV_OK;
   LV_CHECK_ARG(static_cast<long long>(a0.n) * (a0.w + 1) < (1ll << 30), "conv row kernel: batch x width too large");
-  if (a0.cin == 48) return launch_row<48, 48, 8, 3>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
-  return launch_row<64, 64, 4, 2>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
+  if (a0.cin == 48) return launch_row<48, 48, 5, 3>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
+  return launch_row<64, 64, 2, 2>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
 }
 
 }  // namespace lv

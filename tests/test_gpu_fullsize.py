@@ -113,12 +113,14 @@ def test_full_training_step_matches_reference_autograd(v2, n, p, precision):
         worst_r, worst_c = max(worst_r, r), min(worst_c, c)
         num += float(np.sum((got - ref) ** 2))
         den += float(np.sum(ref ** 2))
-        # fp32 mode has no activation rounding, hence no ReLU-mask / L1-sign flips: tight.  bf16: flips of the
-        # discontinuous ReLU mask / L1 sign move a gradient by ~2*sqrt(flipped fraction); budget as in test_gpu_network
-        assert r <= (2e-3 if precision == 'fp32' else 0.15), (name, r)
-        assert c >= (0.99999 if precision == 'fp32' else 0.985), (name, c)
+        # fp32 mode has no activation rounding, hence no ReLU-mask / L1-sign flips: tight.  bf16: measured on B200 at
+        # these sizes (band-limited images): whole arena 3.5e-3, worst tensor 9e-3, worst cosine 0.99996 -- the 2.5-5 %
+        # seen in test_gpu_network come from white-noise inputs on 12x10-pixel images, where a flipped ReLU mask / L1
+        # sign is a large fraction of the few hundred terms of a gradient
+        assert r <= (2e-3 if precision == 'fp32' else 2e-2), (name, r)      # rel-L2 <= 2e-2 for bf16
+        assert c >= (0.99999 if precision == 'fp32' else 0.9995), (name, c)
     total = (num / den) ** 0.5
-    assert total <= (1e-3 if precision == 'fp32' else 0.08), total
+    assert total <= (1e-3 if precision == 'fp32' else 1e-2), total
     print(f'{"cfg4" if v2 else "cfg2"} {precision}: loss {loss:.6f} vs {ref_loss:.6f}; grads vs {_ref_kind()}: '
           f'whole-arena rel-L2 {total:.3e}, worst tensor rel-L2 {worst_r:.3e}, worst cos {worst_c:.6f}')
 
@@ -148,7 +150,21 @@ def test_cfg3_edsr_1080p_matches_reference(precision):
         assert err <= 1e-4 * max(255.0, scale), (err, scale)
     else:
         assert err <= max(2.0, 2.0 / 255.0 * scale), (err, scale)
-        assert rel_l2(out, ref) <= 5e-3
+        r_row = rel_l2(out, ref)
+        assert r_row <= 2e-2, r_row                      # 39 bf16 layers with amplifying default-init weights
+        # the row-marching body chain (taken at this size) must be as accurate as the 16x8-tile kernels
+        import os
+        os.environ['LARVANET_B200_ROW'] = '0'
+        try:
+            m2 = importlib.import_module('models.edsr').create_model()
+            m2.parse_args(['--edsr_conv_features=64', '--edsr_res_blocks=16', '--precision=bf16'])
+            m2.prepare(is_training=False, scales=[4])
+            load_params(m2.get_model(), params)
+            r_tile = rel_l2(m2.upscale(list(lr), 4), ref)
+        finally:
+            del os.environ['LARVANET_B200_ROW']
+        print(f'cfg3 bf16 rel-L2 vs reference: row path {r_row:.3e}, tile path {r_tile:.3e}')
+        assert r_row <= 1.5 * r_tile + 1e-4, (r_row, r_tile)
     print(f'cfg3 {precision}: max|err| {err:.4f} at output scale {scale:.1f} vs {_ref_kind()}')
 
 
