@@ -15,8 +15,10 @@
 //     rows y+1, y, y-1 at once and the sum over the vertical taps happens inside the tensor core: no shuffle epilogue
 //     (conv_tc_ky.cu's problem), 9 MMAs of 73 clk per row (tensor bound) instead of 27 of 45.  An output row is complete --
 //     and drained by an epilogue group while the MMA warp marches on -- once input row y+1 has been issued.
-//     The first MMA that touches a block must overwrite, the others accumulate; the flag is per instruction, so the first
-//     (kx=0, k-step 0) MMA of a row is split in two (N=48 overwrite + N=96 accumulate), as are MMAs at the ring's wrap.
+//     A block is (re)initialised by a tiny MMA of its own -- D = ones[128 x 16] x bias_tile[16 x cout], overwrite mode -- issued
+//     before the first row that touches it: the conv bias (split into bf16 hi + lo parts in two K columns, ~fp32 exact)
+//     is then already in the accumulator, every other MMA accumulates, and the epilogue has no bias to fetch (any load
+//     or shuffle there queues behind the MMAs' operand reads: ~300 clk each, measured).
 //
 // Work unit ("job") = one strip x `rows_per_job` rows; a job of R rows reads R+2 input rows, each ONCE, through a ring of
 // row buffers ([8-channel chunk][130 px][16 B] = the SWIZZLE_NONE K-major A operand; the horizontal tap is a 16-byte shift of
@@ -56,19 +58,21 @@ constexpr int kPubWarp = kProdWarp0 + kProdThreads / 32;  // 12
 constexpr int kThreads = (kPubWarp + 1) * 32;             // 416
 constexpr int kCmdSlots = 4;
 
-// one row of MMA work, written by the scheduler thread, read by the issuer thread (64 bytes)
+// one row of MMA work, written by the scheduler thread, read by the issuer thread
 struct __align__(16) RowCmd {
-  uint32_t a_lo, b_lo;                 // low words of the A / B shared-memory descriptors (start address fields)
-  uint32_t ra_d, ra_b, ra_i, fa_i;     // run A: TMEM address, weight-row offset, idesc; idesc of its first-MMA form
-  uint32_t fc_d, fc_b, fc_i;           // tail of run A for the first MMA (when target 0 is cut off), fc_i == 0: none
-  uint32_t rb_d, rb_b, rb_i;           // run B (ring wrap), rb_i == 0: none
-  uint32_t acc;                        // bit 0: first MMA of run A accumulates, bit 1: first MMA of run B accumulates
+  uint32_t a_lo, b_lo;                 // low words of the A / B shared-memory descriptors (start address + LBO fields)
+  uint32_t ra_d, ra_b;                 // run A: TMEM address, weight-row offset
+  uint32_t ra_i;                       // run A: instruction descriptor (N = cout x targets)
+  uint32_t rb_d, rb_b, rb_i;           // run B (only when the accumulator ring wraps inside the row's targets), rb_i == 0: none
+  uint32_t f0_d, f1_d;                 // blocks this row touches first: initialised with the bias MMA (kNoBlock: none)
   uint32_t bars;                       // barrier INDICES (8 bits each; +1, 0 = none, for all but the first):
                                        //   [0:8) row buffer free, [8:16) / [16:24) accumulator complete (output row yi-1 /
                                        //   row yi on the image's bottom row), [24:32) weight buffer free (layer's last row)
-  uint32_t pad0, pad1;
+  uint32_t bias_lo;                    // low word of the bias tile's descriptor
+  uint32_t pad[4];
 };
-static_assert(sizeof(RowCmd) == 64, "RowCmd is four 16-byte shared-memory loads");
+static_assert(sizeof(RowCmd) == 64, "RowCmd is read with 16-byte shared-memory loads");
+constexpr uint32_t kNoBlock = 0xffffffffu;
 constexpr uint32_t kCmdStop = 0xffffffffu;   // a_lo of the terminating command
 
 struct Params {
@@ -103,10 +107,12 @@ struct Cfg {
   static constexpr int RING = (512 / NT) & ~1;       // accumulator blocks (even: block parity == epilogue group)
   static constexpr int TMEM_COLS = 512;
   static constexpr int PIECES = (kRowPx * CH + kProdThreads - 1) / kProdThreads;
-  static constexpr int NBARS = 2 * NSTAGE + 2 * RING + 2 * WBUFS + 4 + 2 * kCmdSlots;
+  static constexpr int ONES_TILE = 2 * kLanes * 16;  // A operand of the bias MMA: [2 K-halves][128 rows][16 B], (1,1,0,..) / 0
+  static constexpr int BIAS_TILE = 2 * NT * 16;      // B operand: [2 K-halves][cout rows][16 B], row n = (hi(b_n), lo(b_n), 0,..)
+  static constexpr int NBARS = 2 * NSTAGE + 2 * RING + 3 * WBUFS + 4 + 2 * kCmdSlots;
   static constexpr size_t smem_bytes() {
-    return static_cast<size_t>(WBUFS) * W_LAYER + static_cast<size_t>(NSTAGE) * A_STAGE + kCmdSlots * sizeof(RowCmd) +
-           NBARS * 8 + 64;
+    return static_cast<size_t>(WBUFS) * (W_LAYER + BIAS_TILE) + ONES_TILE + static_cast<size_t>(NSTAGE) * A_STAGE +
+           kCmdSlots * sizeof(RowCmd) + NBARS * 8 + 64;
   }
 };
 
@@ -165,11 +171,11 @@ constexpr int kKindPs4 = 100, kKindGeneric = -1;
 
 // Planar epilogue of one output row for one thread (one pixel x NT channels), straight-line for a compile-time flag set
 // EPI (bit0 ReLU, bit1 ReLU-mask, bit2 res1, bit3 res2).  Same arithmetic as chain::fast_tile, but the accumulator is read
-// and processed in two halves of NT/2 channels and the bias arrives by warp shuffle: ~100 live registers instead of ~170,
-// so the 416-thread CTA (128 registers per thread) does not spill in its hot loop.  All operand loads of the row are issued
+// and processed in two halves of NT/2 channels and the bias is already in the accumulator (bias MMA): ~100 live registers
+// instead of ~170, so the 416-thread CTA (128 registers per thread) does not spill in its hot loop.  All operand loads of the row are issued
 // before the accumulator wait (their latency hides behind the MMAs).
 template <int EPI, int NT>
-__device__ __forceinline__ void row_tile(const chain::FastEpi& e, float bias_a, float bias_b, bool valid, size_t o0,
+__device__ __forceinline__ void row_tile(const chain::FastEpi& e, bool valid, size_t o0,
                                          size_t chunk_stride, uint32_t taddr, uint32_t tfull, uint32_t tempty, uint32_t parity,
                                          long long* dbg = nullptr) {
   long long d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;
@@ -212,19 +218,12 @@ __device__ __forceinline__ void row_tile(const chain::FastEpi& e, float bias_a, 
       mbar_arrive(tempty);   // accumulator block free: the MMAs of a later row may overwrite it
     }
     if (dbg != nullptr && h == 1) d4 -= 0;
-    {
+    if (valid) {
       __nv_bfloat16* po = e.out + o0;
 #pragma unroll
       for (int jj = 0; jj < HC; ++jj) {
         const int j = h * HC + jj;
         float* vj = v + 8 * jj;
-        // bias: lane l of every warp keeps bias[l] and bias[32 + l] in two registers and the values travel by warp
-        // shuffle -- any load here (L1 or shared memory) would queue behind the MMAs' operand reads (~300 clk each)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = 8 * j + i;
-          vj[i] += __shfl_sync(0xffffffffu, c < 32 ? bias_a : bias_b, c & 31);
-        }
         if constexpr (do_relu) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) vj[i] = fmaxf(vj[i], 0.f);
@@ -247,7 +246,7 @@ __device__ __forceinline__ void row_tile(const chain::FastEpi& e, float bias_a, 
 #pragma unroll
           for (int t = 0; t < 4; ++t) { vj[2 * t] += bf16_lo(w4[t]); vj[2 * t + 1] += bf16_hi(w4[t]); }
         }
-        if (valid) store8(po + j * chunk_stride, vj);
+        store8(po + j * chunk_stride, vj);
       }
     }
     if (dbg != nullptr && h == 0) d4 = -clock64() + 0;   // start of the second half: d4 becomes (t_ld1_done - t_half0_done)
@@ -277,10 +276,6 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
   float loss = 0.f;
   long long st_wait = 0, st_drain = 0, st_rows = 0;   // debug counters (registers; flushed once per layer)
   long long dbgv[5] = {0, 0, 0, 0, 0};
-  const float* bias_g = a.bias;
-  // this lane's two bias values for row_tile's shuffle broadcast (channels lane and 32 + lane)
-  const float bias_a = (a.bias != nullptr && cx.lane < NT) ? __ldg(a.bias + cx.lane) : 0.f;
-  const float bias_b = (a.bias != nullptr && 32 + cx.lane < NT) ? __ldg(a.bias + 32 + cx.lane) : 0.f;
   for (int job = first; job < cx.g.total_jobs; job += cx.G) {
     const int bk = job / cx.g.nstrips, u = job - bk * cx.g.nstrips;
     const int y0 = bk * cx.g.rows_per_job;
@@ -311,7 +306,7 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
         c1 = clock64();
       }
       if constexpr (KIND == kKindPs4) {
-        loss += chain::ps4_tile<NT>(a, bias_g, valid, n, yo, x, cx.g.H, cx.g.W, o0, cx.chunk_stride, taddr, tfull, tempty, par);
+        loss += chain::ps4_tile<NT>(a, nullptr, valid, n, yo, x, cx.g.H, cx.g.W, o0, cx.chunk_stride, taddr, tfull, tempty, par);
       } else if constexpr (KIND == kKindGeneric) {
         mbar_wait_relaxed(tfull, par);
         tc_fence_after_sync();
@@ -320,12 +315,12 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
           float v[16];
           tmem_ld16(taddr + j * 16, v);
           tmem_ld_wait();
-          if (valid) loss += conv_epilogue16<__nv_bfloat16>(a, n, yo, x, j * 16, v);
+          if (valid) loss += conv_epilogue16<__nv_bfloat16, false>(a, n, yo, x, j * 16, v);   // bias: in the accumulator
         }
         tc_fence_before_sync();
         mbar_arrive(tempty);
       } else {
-        row_tile<KIND, NT>(fe, bias_a, bias_b, valid, o0, cx.chunk_stride, taddr, tfull, tempty, par, st ? dbgv : nullptr);
+        row_tile<KIND, NT>(fe, valid, o0, cx.chunk_stride, taddr, tfull, tempty, par, st ? dbgv : nullptr);
       }
       if (st) {
         st_wait += c1 - c0;
@@ -374,7 +369,9 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
   const int lane = threadIdx.x & 31;
 
   uint8_t* sW = smem;
-  uint8_t* sA = sW + WBUFS * C_::W_LAYER;
+  uint8_t* sBias = sW + WBUFS * C_::W_LAYER;                 // [WBUFS] bias tiles, same ring as the weight buffers
+  uint8_t* sOnes = sBias + WBUFS * C_::BIAS_TILE;
+  uint8_t* sA = sOnes + C_::ONES_TILE;
   RowCmd* cmds = reinterpret_cast<RowCmd*>(sA + NSTAGE * C_::A_STAGE);
   uint64_t* bars = reinterpret_cast<uint64_t*>(cmds + kCmdSlots);
   const uint32_t bar0 = smem_u32(bars);
@@ -384,12 +381,13 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
   auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + RING + b); };
   auto wfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + b); };
   auto wfree_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + WBUFS + b); };
-  auto pub_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + s); };
+  auto bfull_bar = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + b); };
+  auto pub_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 3 * WBUFS + s); };
   auto empty_idx = [&](int s) { return static_cast<uint32_t>(NSTAGE + s); };
   auto tfull_idx = [&](uint32_t b) { return static_cast<uint32_t>(2 * NSTAGE) + b; };
   auto wfree_idx = [&](int b) { return static_cast<uint32_t>(2 * NSTAGE + 2 * RING + WBUFS + b); };
-  auto cmd_full_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + 4 + s); };
-  auto cmd_free_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 2 * WBUFS + 4 + kCmdSlots + s); };
+  auto cmd_full_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 3 * WBUFS + 4 + s); };
+  auto cmd_free_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 3 * WBUFS + 4 + kCmdSlots + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C_::NBARS);
   uint32_t* s_last = tmem_slot + 1;
   volatile uint32_t* pub_seen = tmem_slot + 2;   // rows whose completion the publisher warp has observed
@@ -406,6 +404,7 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
     for (int b = 0; b < WBUFS; ++b) {
       mbar_init(wfull_bar(b), 1);
       mbar_init(wfree_bar(b), 1);
+      mbar_init(bfull_bar(b), kProdThreads);
     }
     for (int s = 0; s < 4; ++s) mbar_init(pub_bar(s), kEpiWarps / 2);
     for (int s = 0; s < kCmdSlots; ++s) {
@@ -415,6 +414,13 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
     tmem_slot[2] = 0u;
     mbar_fence_init();
   }
+  // constant A operand of the bias MMA: K columns 0 and 1 are ones (they meet the bias' hi and lo parts), the rest zero;
+  // the bias tiles start out all zero (only the first K-half of a row is ever rewritten)
+  for (int i = threadIdx.x; i < C_::ONES_TILE / 16; i += kThreads)
+    st_shared_v4(smem_u32(sOnes) + i * 16, make_uint4(i < kLanes ? 0x3f803f80u : 0u, 0u, 0u, 0u));
+  for (int i = threadIdx.x; i < WBUFS * C_::BIAS_TILE / 16; i += kThreads)
+    st_shared_v4(smem_u32(sBias) + i * 16, make_uint4(0u, 0u, 0u, 0u));
+  fence_proxy_async_smem();   // generic-proxy writes above -> UMMA (async proxy) reads
   if (warp == kMmaWarp) tmem_alloc<C_::TMEM_COLS>(smem_u32(tmem_slot));
   tc_fence_before_sync();
   __syncthreads();
@@ -463,6 +469,23 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
     pdl_wait();
     for (int l = 0; l < nlayers; ++l) {
       const __nv_bfloat16* src_base = reinterpret_cast<const __nv_bfloat16*>(P.layer[l].src[0]);
+      {
+        // this layer's bias tile (B operand of the bias MMA): row n = (hi(b_n), lo(b_n), 0, ...), b_n = hi + lo in bf16.
+        // It shares the weight ring's slot: free once the MMAs of layer l - WBUFS have retired (every CTA has at least
+        // one job per layer, so that layer's last row did commit `wfree`).
+        const int wb = l % WBUFS;
+        if (l >= WBUFS) mbar_wait_relaxed(wfree_bar(wb), ((l / WBUFS) - 1) & 1);
+        if (ptid < NT) {
+          const float* bias = P.layer[l].bias;
+          const float b = (bias != nullptr && ptid < P.layer[l].cout) ? __ldg(bias + ptid) : 0.f;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+          const uint32_t w = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+          st_shared_v4(smem_u32(sBias + wb * C_::BIAS_TILE) + ptid * 16, make_uint4(w, 0u, 0u, 0u));
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(bfull_bar(wb));
+      }
       for (int job = first_job(l); job < g.total_jobs; job += G) {
         const Job j = decode(job);
         // this thread's 16-byte pieces of a row buffer: piece idx = chunk * 130 + px  <->  shared-memory offset idx * 16
@@ -530,20 +553,19 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
       load_weights(0);   // packed weights are never written while a launch chain is in flight: no pdl_wait needed
       uint32_t fill = 0, k = 0, ncmd = 0;
       long long ss_setup = 0, ss_tempty = 0, ss_full = 0, ss_slot = 0, ss_rows = 0;   // debug counters (registers)
-      uint32_t free_pending = 0, free_phase = 0;   // bit b: MMAs reading weight buffer b outstanding / wfree parity
       for (int l = 0; l < nlayers; ++l) {
         const int wb = l % WBUFS;
         if (l + 1 < nlayers) {
+          // the next layer's weights go to the slot of layer l + 1 - WBUFS: wait until its MMAs have retired (every CTA
+          // has at least one job per layer: grid <= jobs, so each layer's last row commits `wfree` exactly once)
           const int nb = (l + 1) % WBUFS;
-          if (free_pending & (1u << nb)) {
-            mbar_wait(wfree_bar(nb), (free_phase >> nb) & 1u);
-            free_phase ^= 1u << nb;
-            free_pending &= ~(1u << nb);
-          }
+          if (l + 1 >= WBUFS) mbar_wait(wfree_bar(nb), (((l + 1) / WBUFS) - 1) & 1);
           load_weights(l + 1);
         }
         mbar_wait(wfull_bar(wb), (l / WBUFS) & 1);
+        mbar_wait(bfull_bar(wb), (l / WBUFS) & 1);
         const uint32_t b_lo = static_cast<uint32_t>(umma_smem_desc(smem_u32(sW + wb * C_::W_LAYER), C_::W_PLANE, 128));
+        const uint32_t bias_lo = static_cast<uint32_t>(umma_smem_desc(smem_u32(sBias + wb * C_::BIAS_TILE), NT * 16, 128));
         // the layer's last row of this CTA also commits the "weight buffer free" barrier: find it first
         int last_job = -1;
         for (int job = first_job(l); job < g.total_jobs; job += G) last_job = job;
@@ -565,30 +587,26 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
             const uint32_t kk0 = k + static_cast<uint32_t>(yi + 1 - j.y0);      // target 0 (may be "virtual" when invalid)
             auto col_of = [&](int t) { return (RING - 1 - ((kk0 - static_cast<uint32_t>(t)) % RING)) * NT; };
             // Runs = maximal groups of valid targets issued as ONE MMA (adjacent blocks, N = NT * targets): A = [ta..ea],
-            // B = [ea+1..tb] (only when the ring wraps inside the interval).  The row's first MMA (kx = 0, k-step 0)
-            // must additionally separate blocks it OVERWRITES (first contribution to that output row: target 0 always,
-            // target 1 on the image's top row) from blocks it accumulates into -- the flag is per instruction -- so
-            // run A is cut after target 0 when the rest accumulates.
+            // B = [ea+1..tb] (only when the ring wraps inside the interval).  Blocks that get their FIRST contribution
+            // from this input row (target 0 always; target 1 too on the image's top row) are initialised by the bias MMA.
             int ea = ta;
             while (ea < tb && ((kk0 - static_cast<uint32_t>(ea)) % RING) != 0) ++ea;
             const bool has_b = ea < tb;
-            const bool cut = yi > 0 && ta == 0 && ea > 0;
+            const bool fresh0 = ta == 0, fresh1 = yi == 0 && ta <= 1 && tb >= 1;
             const int stage = fill % NSTAGE;
-            const uint32_t ra_i = idesc_n((ea - ta + 1) * NT);
             const uint32_t tfa = (yi - 1 >= j.y0 && yi - 1 < j.y1) ? 1u + tfull_idx((k + static_cast<uint32_t>(yi - 1 - j.y0)) % RING) : 0u;
             const uint32_t tfb = (yi == g.H - 1 && yi >= j.y0 && yi < j.y1) ? 1u + tfull_idx((k + static_cast<uint32_t>(yi - j.y0)) % RING) : 0u;
             const uint32_t wfr = (job == last_job && yi == yb - 1) ? 1u + wfree_idx(wb) : 0u;
             const uint4 q0 = make_uint4(static_cast<uint32_t>(umma_smem_desc(smem_u32(sA + stage * C_::A_STAGE), C_::A_PLANE, 128)),
                                         b_lo, tmem_base + col_of(ta), static_cast<uint32_t>(ta * NT));
-            const uint4 q1 = make_uint4(ra_i, cut ? idesc_n(NT) : ra_i, tmem_base + col_of(1), static_cast<uint32_t>(NT));
-            const uint4 q2 = make_uint4(cut ? idesc_n(ea * NT) : 0u, tmem_base + col_of(ea + 1), static_cast<uint32_t>((ea + 1) * NT),
+            const uint4 q1 = make_uint4(idesc_n((ea - ta + 1) * NT), tmem_base + col_of(ea + 1), static_cast<uint32_t>((ea + 1) * NT),
                                         has_b ? idesc_n((tb - ea) * NT) : 0u);
-            const uint4 q3 = make_uint4(((yi == 0 || ta == 0) ? 0u : 1u) | ((yi == 0) ? 0u : 2u),
-                                        empty_idx(stage) | (tfa << 8) | (tfb << 16) | (wfr << 24), 0u, 0u);
+            const uint4 q2 = make_uint4(fresh0 ? tmem_base + col_of(0) : kNoBlock, fresh1 ? tmem_base + col_of(1) : kNoBlock,
+                                        empty_idx(stage) | (tfa << 8) | (tfb << 16) | (wfr << 24), bias_lo);
             const long long c1 = stat_clk(g);
-            // blocks overwritten by this row must have been drained by the epilogue (their previous output row)
-            if (ta == 0) mbar_wait(tempty_bar(kk0 % RING), ((kk0 / RING) & 1u) ^ 1u);
-            if (yi == 0 && tb >= 1) {
+            // blocks initialised by this row must have been drained by the epilogue (their previous output row)
+            if (fresh0) mbar_wait(tempty_bar(kk0 % RING), ((kk0 / RING) & 1u) ^ 1u);
+            if (fresh1) {
               const uint32_t kk1 = kk0 - 1u;
               mbar_wait(tempty_bar(kk1 % RING), ((kk1 / RING) & 1u) ^ 1u);
             }
@@ -601,7 +619,6 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
             st_shared_v4(smem_u32(dst), q0);
             st_shared_v4(smem_u32(dst + 1), q1);
             st_shared_v4(smem_u32(dst + 2), q2);
-            st_shared_v4(smem_u32(dst + 3), q3);
             mbar_arrive(cmd_full_bar(slot));   // release: the command (and the barrier completions observed above)
             if (g.stats != nullptr) {
               ss_setup += c1 - c0; ss_tempty += c2 - c1; ss_full += c3 - c2; ss_slot += clock64() - c3; ss_rows += 1;
@@ -609,7 +626,6 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
           }
           k += static_cast<uint32_t>(j.y1 - j.y0);
         }
-        if (last_job >= 0) free_pending |= 1u << wb;
       }
       // terminating command
       {
@@ -629,6 +645,7 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
       // high word of both operand descriptors: SBO = 128 B (8 rows x 16 B core matrices), descriptor version 1; the low
       // word (start address + LBO) comes with the command
       constexpr uint64_t kDescHi = (static_cast<uint64_t>((128 >> 4) & 0x3fff) << 32) | (static_cast<uint64_t>(1) << 46);
+      const uint64_t ones_desc = umma_smem_desc(smem_u32(sOnes), kLanes * 16, 128);
       for (uint32_t n = 0;; ++n) {
         const uint32_t slot = n % kCmdSlots;
         const long long c0 = stat_clk(g);
@@ -636,16 +653,18 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
         const uint32_t ca = smem_u32(&cmds[slot]);
         const uint4 w0 = ld_shared_v4(ca);
         if (w0.x == kCmdStop) break;
-        const uint4 w1 = ld_shared_v4(ca + 16), w2 = ld_shared_v4(ca + 32), w3 = ld_shared_v4(ca + 48);
+        const uint4 w1 = ld_shared_v4(ca + 16), w2 = ld_shared_v4(ca + 32);
         mbar_arrive(cmd_free_bar(slot));
         fence_proxy_async_smem();   // cp.async (generic proxy) writes of the row -> UMMA (async proxy) reads
         tc_fence_after_sync();
         const long long c1 = stat_clk(g);
-        // RowCmd fields: w0 = {a_lo, b_lo, ra_d, ra_b}, w1 = {ra_i, fa_i, fc_d, fc_b}, w2 = {fc_i, rb_d, rb_b, rb_i},
-        // w3 = {acc, empty_bar, tfull_a, tfull_b}
+        // RowCmd fields: w0 = {a_lo, b_lo, ra_d, ra_b}, w1 = {ra_i, rb_d, rb_b, rb_i}, w2 = {f0_d, f1_d, bars, bias_lo}
         const uint64_t adesc0 = kDescHi | w0.x;
         const uint64_t bdesc0 = kDescHi | w0.y;
-        const bool cut = w2.x != 0u, has_b = w2.w != 0u;
+        const bool has_b = w1.w != 0u;
+        // blocks that get their first contribution from this row: D = ones x bias tile (overwrite)
+        if (w2.x != kNoBlock) umma_bf16(w2.x, ones_desc, kDescHi | w2.w, idesc_n(NT), 0u);
+        if (w2.y != kNoBlock) umma_bf16(w2.y, ones_desc, kDescHi | w2.w, idesc_n(NT), 0u);
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
@@ -653,18 +672,12 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
             // descriptor start addresses move in 16-byte units: horizontal tap = one pixel, k-step = two chunk planes
             const uint64_t adesc = adesc0 + static_cast<uint64_t>((kx * 16 + 2 * ks * C_::A_PLANE) >> 4);
             const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((kx * C_::W_KX + 2 * ks * C_::W_PLANE) >> 4);
-            if (kx == 0 && ks == 0) {
-              umma_bf16(w0.z, adesc, bdesc + w0.w, w1.y, w3.x & 1u);
-              if (cut) umma_bf16(w1.z, adesc, bdesc + w1.w, w2.x, 1u);
-              if (has_b) umma_bf16(w2.y, adesc, bdesc + w2.z, w2.w, (w3.x >> 1) & 1u);
-            } else {
-              umma_bf16(w0.z, adesc, bdesc + w0.w, w1.x, 1u);
-              if (has_b) umma_bf16(w2.y, adesc, bdesc + w2.z, w2.w, 1u);
-            }
+            umma_bf16(w0.z, adesc, bdesc + w0.w, w1.x, 1u);
+            if (has_b) umma_bf16(w1.y, adesc, bdesc + w1.z, w1.w, 1u);
           }
         }
         const long long c2 = stat_clk(g);
-        const uint32_t bi = w3.y;
+        const uint32_t bi = w2.z;
         umma_commit(bar0 + 8u * (bi & 0xffu));                                         // row buffer reusable once these MMAs retire
         if ((bi >> 8) & 0xffu) umma_commit(bar0 + 8u * (((bi >> 8) & 0xffu) - 1u));    // output row yi-1 complete
         if ((bi >> 16) & 0xffu) umma_commit(bar0 + 8u * (((bi >> 16) & 0xffu) - 1u));  // image's bottom row: row yi complete

@@ -205,7 +205,7 @@ class LarvaEngine:
         self._chain = None      # list of pending ConvArgs while a chain is being recorded
         self._chain_ws = {}     # (n, h, w) -> flag workspace
         self._row_active = False  # the pass being recorded uses the row-marching kernel (ky-stacked operands)
-        self.row_min_pixels = int(os.environ.get('LARVANET_B200_ROW_MIN_PIXELS', str(768 * 1024)))
+        self.row_min_pixels = int(os.environ.get('LARVANET_B200_ROW_MIN_PIXELS', str(640 * 1024)))
         self.replayed_launches = 0  # kernels executed through CUDA-graph replays (lv_launch_count only sees eager ones)
         # data parallel
         self.world_size = 1
@@ -817,7 +817,7 @@ class EdsrEngine:
                 self._pk[(p, 'ky')] = self._packed_ky[k * step:k * step + nb_]
             self._pack_items += [dict(w=self.arena.views[p + '.weight'], packed=self._pk[(p, 'ky')], transpose=0, i_off=0,
                                       i_cnt=f, cin=f, dtype=act_dtype, wlayout=_lib.LV_W_KY_STACKED) for p in self._body]
-        self.row_min_pixels = int(os.environ.get('LARVANET_B200_ROW_MIN_PIXELS', str(768 * 1024)))
+        self.row_min_pixels = int(os.environ.get('LARVANET_B200_ROW_MIN_PIXELS', str(640 * 1024)))
         self._chain_ws = {}
         self._packed_version = None
         self._infer = _ShapeCache(int(os.environ.get('LARVANET_B200_SHAPE_CACHE', '4')))
