@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LV_ABI_VERSION 1
+#define LV_ABI_VERSION 2
 
 enum { LV_F32 = 0, LV_BF16 = 1 };
 
@@ -166,9 +166,12 @@ int lv_head_bicubic_fwd(const float* x, const float* w, const float* b, const fl
                         void* fea, float* base_hr, int n, int h, int w_, int cout, int dtype, void* stream);
 /* bicubic x4 only (LarvaNetModule.base, models/LarvaNet.py:283-285) */
 int lv_bicubic_x4(const float* x, float* base_hr, int n, int c, int h, int w_, void* stream);
-/* head weight/bias gradient: dw[cout,3,3,3] += scale*sum_px dy*x, db += scale*sum dy (autograd of :227) */
+/* head weight/bias gradient (autograd of :227): dw[cout,3,3,3] = scale*sum_px dy*x, db = scale*sum dy when `overwrite`,
+ * else accumulated into dw / db.  Deterministic two-pass reduction (no atomics); `workspace` holds the per-block partial
+ * sums: lv_head_wgrad_workspace_bytes(cout) bytes. */
+int64_t lv_head_wgrad_workspace_bytes(int cout);
 int lv_head_wgrad(const float* x, const void* dy, float* dw, float* db, int n, int h, int w_, int cout,
-                  int dtype, float scale, void* stream);
+                  int dtype, float scale, void* workspace, int64_t workspace_bytes, int overwrite, void* stream);
 
 /*
  * Batched weight gradients.  `items_dev` is a DEVICE array of `count` items (same dtype; bf16 needs cin == 48);

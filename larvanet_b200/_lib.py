@@ -17,7 +17,7 @@ LV_EPI_NHWC, LV_EPI_PS4_NCHW, LV_EPI_PS2_NHWC, LV_EPI_RGB_NCHW = 0, 1, 2, 3
 LV_MAX_SRC = 4
 LV_W_TAP_MAJOR, LV_W_KY_STACKED = 0, 1
 LV_CHAIN_MAX_LAYERS = 96
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class LarvaNetB200Error(RuntimeError):
@@ -76,7 +76,8 @@ SIGNATURES = {
     'lv_conv3x3_chain': (C.c_int, [C.POINTER(ConvArgs), C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     'lv_head_bicubic_fwd': (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p]),
     'lv_bicubic_x4': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    'lv_head_wgrad': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_float, C.c_void_p]),
+    'lv_head_wgrad_workspace_bytes': (C.c_int64, [C.c_int]),
+    'lv_head_wgrad': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 5 + [C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     'lv_wgrad_workspace_bytes': (C.c_int64, [C.POINTER(WgradItem), C.c_int, C.c_int]),
     'lv_conv3x3_wgrad': (C.c_int, [C.POINTER(WgradItem), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'lv_conv3x3_wgrad_simt': (C.c_int, [C.POINTER(WgradItem), C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

@@ -52,7 +52,8 @@ extern int g_use_pdl;
 int head_bicubic_fwd(const float*, const float*, const float*, const float*, const float*, void*, float*, int, int, int, int,
                      int, cudaStream_t);
 int bicubic_x4(const float*, float*, int, int, int, int, cudaStream_t);
-int head_wgrad(const float*, const void*, float*, float*, int, int, int, int, int, float, cudaStream_t);
+long long head_wgrad_workspace_bytes(int);
+int head_wgrad(const float*, const void*, float*, float*, int, int, int, int, int, float, void*, long long, int, cudaStream_t);
 int pack_weights(const lv_pack_item*, int, cudaStream_t);
 int nchw_to_nhwc(const float*, void*, int, int, int, int, int, cudaStream_t);
 int nhwc_to_nchw(const void*, float*, int, int, int, int, int, cudaStream_t);
@@ -200,10 +201,13 @@ int lv_bicubic_x4(const float* x, float* base_hr, int n, int c, int h, int w_, v
   return bicubic_x4(x, base_hr, n, c, h, w_, static_cast<cudaStream_t>(stream));
 }
 
+int64_t lv_head_wgrad_workspace_bytes(int cout) { return cout > 0 ? head_wgrad_workspace_bytes(cout) : -1; }
+
 int lv_head_wgrad(const float* x, const void* dy, float* dw, float* db, int n, int h, int w_, int cout, int dtype,
-                  float scale, void* stream) {
+                  float scale, void* workspace, int64_t workspace_bytes, int overwrite, void* stream) {
   LV_CHECK_ARG(x && dy && dw, "head wgrad: null pointer");
-  return head_wgrad(x, dy, dw, db, n, h, w_, cout, dtype, scale, static_cast<cudaStream_t>(stream));
+  return head_wgrad(x, dy, dw, db, n, h, w_, cout, dtype, scale, workspace, workspace_bytes, overwrite,
+                    static_cast<cudaStream_t>(stream));
 }
 
 int64_t lv_wgrad_workspace_bytes(const lv_wgrad_item* items_host, int count, int splits) {

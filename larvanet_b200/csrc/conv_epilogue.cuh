@@ -122,4 +122,29 @@ __device__ __forceinline__ float conv_epilogue16(const lv_conv_args& a, int n, i
   return loss;
 }
 
+// PixelShuffle(2) epilogue for 32 consecutive conv channels of one pixel (bf16 output): they are the 8 consecutive OUTPUT
+// channels co0/4 .. co0/4+7 of the four sub-pixels, i.e. one full 16-byte chunk per sub-pixel -- four vector stores
+// instead of the 64 two-byte stores of the generic 16-channel routine (models/edsr.py:156-173, nn.PixelShuffle(2)).
+// Bias, res_scale and ReLU as in conv_epilogue16; no mask / residual operands (EDSR's UpsampleBlock has none).
+__device__ __forceinline__ void conv_epilogue_ps2_32(const lv_conv_args& a, int n, int y, int x, int co0, float* v) {
+  const int H = a.h, W = a.w, CO = a.cout >> 2;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float b = (a.bias != nullptr) ? __ldg(a.bias + co0 + i) : 0.f;
+    v[i] = a.res_scale * (v[i] + b);
+    if (a.relu) v[i] = fmaxf(v[i], 0.f);
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a.out);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = v[4 * k + 2 * i + j];
+      store8(out + act_off(n, 2 * y + i, 2 * x + j, co0 >> 5, 2 * H, 2 * W, CO >> 3), o);
+    }
+  }
+}
+
 }  // namespace lv

@@ -334,6 +334,23 @@ conv3x3_tc_kernel(const __grid_constant__ lv_conv_args a, const ConvGeom g) {
         // generic path (PixelShuffle / RGB / multi-N-tile / cold shapes): shared 16-channel epilogue
         mbar_wait_relaxed(tfull_bar(as), (k >> 1) & 1);
         tc_fence_after_sync();
+        if constexpr (NT % 32 == 0) {
+          if (a.epilogue == LV_EPI_PS2_NHWC && a.mask == nullptr && a.res1 == nullptr && a.res2 == nullptr &&
+              a.cout == g.cout_pad) {
+            // EDSR UpsampleBlock: 32 conv channels = one 16-byte output chunk per sub-pixel
+#pragma unroll 1
+            for (int j = 0; j < NT / 32; ++j) {
+              float v[32];
+              tmem_ld16(taddr + j * 32, v);
+              tmem_ld16(taddr + j * 32 + 16, v + 16);
+              tmem_ld_wait();
+              if (valid) conv_epilogue_ps2_32(a, n, y, x, ntile * NT + j * 32, v);
+            }
+            tc_fence_before_sync();
+            mbar_arrive(tempty_bar(as));
+            continue;
+          }
+        }
 #pragma unroll 1
         for (int j = 0; j < NT / 16; ++j) {
           float v[16];

@@ -155,14 +155,16 @@ bicubic_kernel(const float* __restrict__ x, float* __restrict__ base_hr, int NC,
   }
 }
 
-// head weight gradient: dw[co][c][ky][kx] += scale * sum_px dy[px][co] * x[c][y+ky-1][x+kx-1];  db[co] += scale * sum dy
-// Persistent blocks loop over 8x16 pixel tiles and keep their partial sums in registers; thread = (pair of output
-// channels, one (c,ky) row of three kx taps): 6 FMAs per 5 shared-memory loads, one atomicAdd per output per block.
+// head weight gradient: dw[co][c][ky][kx] (+)= scale * sum_px dy[px][co] * x[c][y+ky-1][x+kx-1];  db[co] (+)= scale * sum dy
+// Two passes, no atomics (deterministic): blocks loop over 8x16 pixel tiles and keep their partial sums in registers --
+// thread = (pair of output channels, one (c,ky) row of three kx taps): 6 FMAs per 5 shared-memory loads -- and store ONE
+// partial vector [cout*27 + cout] per block; head_wgrad_reduce_kernel sums the blocks' vectors in a fixed order, scales
+// and stores (or adds to) dw / db.  Up to four blocks per SM overlap each other's load and compute phases.
 constexpr int kGW = 16, kGH = 8;  // pixel tile of the head wgrad
 template <typename T>
 __global__ void __launch_bounds__(288)
-head_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, float* __restrict__ db,
-                  int N, int H, int W, int cout, float scale) {
+head_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ partial,
+                  int N, int H, int W, int cout) {
   __shared__ float sx[3][kGH + 2][kGW + 2];
   extern __shared__ float sdy[];  // [kGH*kGW][cout+2]
   const int cp = cout + 2;
@@ -222,13 +224,37 @@ head_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* 
     }
   }
   if (active) {
+    float* pv = partial + static_cast<size_t>(blockIdx.x) * (cout * 28);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int co = 2 * cog + j;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) atomicAdd(dw + co * 27 + kc * 9 + ky * 3 + kx, scale * acc[j][kx]);
-      if (kg == 0 && db != nullptr) atomicAdd(db + co, scale * bacc[j]);
+      for (int kx = 0; kx < 3; ++kx) pv[co * 27 + kc * 9 + ky * 3 + kx] = acc[j][kx];
+      if (kg == 0) pv[cout * 27 + co] = bacc[j];
     }
+  }
+}
+
+// second pass: out[i] (+)= scale * sum over blocks of partial[block][i], i in [0, cout*28): 16 threads per output split the
+// blocks, fixed summation order
+__global__ void __launch_bounds__(1024)
+head_wgrad_reduce_kernel(const float* __restrict__ partial, int nblocks, int nout, int cout, float* __restrict__ dw,
+                         float* __restrict__ db, float scale, int overwrite) {
+  __shared__ float red[16][64];
+  const int o = blockIdx.x * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  float s = 0.f;
+  if (o < nout) {
+    for (int b = part; b < nblocks; b += 16) s += partial[static_cast<size_t>(b) * nout + o];
+  }
+  red[part][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (part == 0 && o < nout) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += red[i][threadIdx.x & 63];
+    t *= scale;
+    float* dst = (o < cout * 27) ? (dw + o) : (db != nullptr ? db + (o - cout * 27) : nullptr);
+    if (dst != nullptr) *dst = overwrite ? t : (*dst + t);
   }
 }
 
@@ -258,22 +284,35 @@ int bicubic_x4(const float* x, float* base_hr, int n, int c, int h, int w_, cuda
   return LV_OK;
 }
 
+constexpr int kHeadWgradMaxBlocks = 4 * 148;
+
+long long head_wgrad_workspace_bytes(int cout) {
+  return static_cast<long long>(kHeadWgradMaxBlocks) * cout * 28 * sizeof(float);
+}
+
 int head_wgrad(const float* x, const void* dy, float* dw, float* db, int n, int h, int w_, int cout, int dtype,
-               float scale, cudaStream_t stream) {
+               float scale, void* workspace, long long workspace_bytes, int overwrite, cudaStream_t stream) {
   if (n == 0 || h == 0 || w_ == 0) return LV_OK;
   LV_CHECK_ARG(cout <= 64 && cout % 2 == 0, "head wgrad: cout must be even and <= 64 (got %d)", cout);
   const long long tiles = static_cast<long long>(n) * ((w_ + kGW - 1) / kGW) * ((h + kGH - 1) / kGH);
   LV_CHECK_ARG(tiles < (1ll << 31), "head wgrad: too many tiles");
-  // one persistent block per SM (measured at 16 x 48x48: 50 / 30 / 23.5 / 29 us for 37 / 74 / 148 / 288 blocks: a tile
-  // costs ~6 us of shared-memory-latency-bound FMAs, the 1,344 atomics per block are secondary)
-  const long long cap = sm_count();
+  // up to four co-resident blocks per SM (shared memory 27 KB, 288 threads): their load / compute phases overlap
+  long long cap = 4ll * sm_count();
+  if (cap > kHeadWgradMaxBlocks) cap = kHeadWgradMaxBlocks;
   const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+  const int nout = cout * 28;
+  LV_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<long long>(grid) * nout * 4,
+               "head wgrad: workspace too small (%lld bytes; lv_head_wgrad_workspace_bytes(cout) gives the size)", workspace_bytes);
+  float* partial = static_cast<float*>(workspace);
   const size_t smem = static_cast<size_t>(kGH * kGW) * (cout + 2) * sizeof(float);
   if (dtype == LV_F32)
-    head_wgrad_kernel<float><<<grid, 288, smem, stream>>>(x, static_cast<const float*>(dy), dw, db, n, h, w_, cout, scale);
+    head_wgrad_kernel<float><<<grid, 288, smem, stream>>>(x, static_cast<const float*>(dy), partial, n, h, w_, cout);
   else
-    head_wgrad_kernel<__nv_bfloat16><<<grid, 288, smem, stream>>>(x, static_cast<const __nv_bfloat16*>(dy), dw, db, n, h,
-                                                                  w_, cout, scale);
+    head_wgrad_kernel<__nv_bfloat16><<<grid, 288, smem, stream>>>(x, static_cast<const __nv_bfloat16*>(dy), partial, n, h,
+                                                                  w_, cout);
+  LV_LAUNCH_OK();
+  head_wgrad_reduce_kernel<<<(nout + 63) / 64, 1024, 0, stream>>>(partial, static_cast<int>(grid), nout, cout, dw, db, scale,
+                                                                  overwrite);
   LV_LAUNCH_OK();
   return LV_OK;
 }

@@ -470,6 +470,7 @@ class LarvaEngine:
             b.mf, b.ut, b.gt, b.dut, b.dmf = (self._act(n, h, w) for _ in range(5))
             b.dfeat = [self._act(n, h, w) for _ in range(self.m)]
         b.exits = None
+        b.head_ws = torch.empty(int(_lib.load().lv_head_wgrad_workspace_bytes(C)), dtype=torch.uint8, device=dev)
         b.row = self.use_row_path(n, h, w)
         # weight-gradient batches, one per body (+ tail), in arena order
         numel = n * 3 * 16 * h * w
@@ -551,11 +552,8 @@ class LarvaEngine:
         b.loss_sum.zero_()
         if self.simt or self.act_dtype != torch.bfloat16:
             self.arena.grad.zero_()           # the CUDA-core weight-gradient kernels accumulate with atomics
-        else:
-            # the tensor-core weight-gradient reduction STORES every conv gradient (items carry overwrite=1); only the
-            # head conv's gradient is accumulated with atomics and needs a zeroed slice
-            lo, hi = self._head_grad_slice
-            self.arena.grad[lo:hi].zero_()
+        # (bf16: the tensor-core weight-gradient reduction and the head gradient's second pass STORE their results --
+        # every gradient has exactly one writer per step -- so nothing needs zeroing)
         ops.head_bicubic(b.x, hw, hb, b.f0, b.base)
         self._begin_chain()
         # ---------------- forward ----------------
@@ -607,7 +605,8 @@ class LarvaEngine:
         for wb in b.wgrad:
             wb.launch(simt=self.simt)
         ops.head_wgrad(b.x, b.dfin[0], self.arena.grad_views['head.feature_extraction.weight'],
-                       self.arena.grad_views['head.feature_extraction.bias'], scale)
+                       self.arena.grad_views['head.feature_extraction.bias'], scale,
+                       overwrite=not (self.simt or self.act_dtype != torch.bfloat16), workspace=b.head_ws)
 
     def train_step(self, x, truth, keep_exits=False):
         """One forward+backward.  Leaves d(loss)/d(param) in the gradient arena (== every param.grad) and returns the

@@ -298,7 +298,6 @@ def train_main(argv=None, epoch_bookkeeping=False):
     log(f'volume {model.volume_per_step/1e6:.2f}M for 1 step.')
     log(f'needs {model_args.val_volume/model.volume_per_step:.0f}steps to validate for {model_args.val_volume/1e9:.1f}G volume.')
     loss = float('nan')
-    import numpy as np
     from larvanet_b200.prefetch import DevicePrefetcher
 
     def host_batches():

@@ -217,12 +217,21 @@ def bicubic_x4(x, out):
           'lv_bicubic_x4')
 
 
-def head_wgrad(x, dy, dw, db, scale):
+_HEAD_WS = {}
+
+
+def head_wgrad(x, dy, dw, db, scale, overwrite=False, workspace=None):
+    """Head conv weight / bias gradient (deterministic two-pass reduction).  `overwrite`: store instead of accumulate."""
     n, c, h, w = (int(v) for v in x.shape)
     cout = act_dims(dy)[3]
+    if workspace is None:      # per-device scratch for callers that do not manage one (tests, module-level calls)
+        key = (x.device.index, cout)
+        if key not in _HEAD_WS:
+            _HEAD_WS[key] = torch.empty(int(_lib.load().lv_head_wgrad_workspace_bytes(cout)), dtype=torch.uint8, device=x.device)
+        workspace = _HEAD_WS[key]
     check(_lib.load().lv_head_wgrad(_ptr(x, torch.float32, 'x'), _ptr(dy, None, 'dy'), _ptr(dw, torch.float32, 'dw'),
                                     _ptr(db, torch.float32, 'db'), n, h, w, cout, dtype_id(dy.dtype), float(scale),
-                                    _stream()), 'lv_head_wgrad')
+                                    workspace.data_ptr(), workspace.numel(), int(bool(overwrite)), _stream()), 'lv_head_wgrad')
 
 
 class WgradBatch:

@@ -217,6 +217,25 @@ def test_wgrad_merge_slices_and_head(prec):
     _, dwh_ref, dbh_ref = O.conv2d_backward(img.astype(np.float64), np.zeros((48, 3, 3, 3)), dyq)
     assert rel_l2(dwh.cpu().numpy(), 0.25 * dwh_ref) < 1e-5
     assert rel_l2(dbh.cpu().numpy(), 0.25 * dbh_ref) < 1e-5
+    # accumulate semantics (second call adds), overwrite semantics (garbage in, gradient out), bitwise determinism of the
+    # two-pass reduction, and a shape with more tiles than resident blocks (ragged edges)
+    ops.head_wgrad(torch.from_numpy(img).cuda(), dy, dwh, dbh, 0.25)
+    assert rel_l2(dwh.cpu().numpy(), 0.5 * dwh_ref) < 1e-5
+    junk_w = torch.full((48, 3, 3, 3), 7.0, device='cuda')
+    junk_b = torch.full((48,), -3.0, device='cuda')
+    ops.head_wgrad(torch.from_numpy(img).cuda(), dy, junk_w, junk_b, 0.25, overwrite=True)
+    assert rel_l2(junk_w.cpu().numpy(), 0.25 * dwh_ref) < 1e-5 and rel_l2(junk_b.cpu().numpy(), 0.25 * dbh_ref) < 1e-5
+    if dtype == torch.bfloat16:
+        n2, h2, w2 = 9, 77, 150
+        dy2, dy2q = _act(rs, n2, 48, h2, w2, dtype)
+        img2 = rs.uniform(0, 255, (n2, 3, h2, w2)).astype(np.float32)
+        a_w, a_b = torch.empty((48, 3, 3, 3), device='cuda'), torch.empty(48, device='cuda')
+        b_w, b_b = torch.empty_like(a_w), torch.empty_like(a_b)
+        ops.head_wgrad(torch.from_numpy(img2).cuda(), dy2, a_w, a_b, 1e-3, overwrite=True)
+        ops.head_wgrad(torch.from_numpy(img2).cuda(), dy2, b_w, b_b, 1e-3, overwrite=True)
+        assert torch.equal(a_w, b_w) and torch.equal(a_b, b_b)
+        _, ref_w, ref_b = O.conv2d_backward(img2.astype(np.float64), np.zeros((48, 3, 3, 3)), dy2q)
+        assert rel_l2(a_w.cpu().numpy(), 1e-3 * ref_w) < 1e-5 and rel_l2(a_b.cpu().numpy(), 1e-3 * ref_b) < 1e-5
 
 
 def test_layout_loss_adamw_helpers():

@@ -14,6 +14,10 @@ def make(blocks, v2):
 def main():
     rank, world, local = lvdist.init_from_env('nccl')
     torch.cuda.set_device(local)
+    # phase 1 checks the gradients right after engine.train_step(): use the stand-alone exchange (two-shot peer kernel or
+    # NCCL); the exchange fused into the optimizer kernel is phase 2
+    fused_env = os.environ.get('LARVANET_B200_DP_FUSED')
+    os.environ['LARVANET_B200_DP_FUSED'] = '0'
     # (v2, global batch): 7 patches do not divide over the ranks -> uneven shards, scaled by the all-reduced global count
     for v2, total in ((False, 8), (True, 8), (False, 7)):
         blocks = [2, 2]
@@ -34,6 +38,10 @@ def main():
         if rank == 0:
             print(f'v2={v2} batch={total} world={world}: loss dp={loss:.6f} single={loss1:.6f} rel grad diff={rel:.3e}', flush=True)
         assert abs(loss - loss1) <= 1e-6 * abs(loss1) and rel < 2e-3, (loss, loss1, rel)
+    if fused_env is None:
+        del os.environ['LARVANET_B200_DP_FUSED']
+    else:
+        os.environ['LARVANET_B200_DP_FUSED'] = fused_env
     # ---- optimizer steps: the fused exchange + AdamW + re-pack kernel (peer memory) against a single process on the
     # global batch, and bit-identical replicas across ranks
     import types
