@@ -90,12 +90,14 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def roofline_traffic(kernel_substr):
+def roofline_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` summary of the final build
+    (profiles/roofline_traffic.json, written from profiles/r02_step_ncu_full_summary.txt); None when there is no record."""
     path = os.path.join(REPO, 'profiles', 'roofline_traffic.json')
     try:
         with open(path) as f:
             for rec in json.load(f):
-                if kernel_substr in rec.get('kernel', ''):
+                if rec.get('key') == key:
                     return rec.get('dram_bytes_per_launch')
     except (OSError, ValueError):
         pass
@@ -378,15 +380,17 @@ def run_ours(a):
         durs = np.array([e0.elapsed_time(e1) for e0, e1, _, _ in recs]) * 1e-3
         fl = np.array([f for _, _, f, _ in recs])
         ach = float(fl.sum() / durs.sum() / 1e12)
-        peak = float(peaks.get('bf16_tflops_sustained', peaks['bf16_tflops']))
+        # the launch is timed ALONE in an otherwise idle eager step (SM clocks at their maximum, no power cap): the
+        # burst figure is the right denominator (the sustained one was measured at 1245 MHz under the 1 kW cap)
+        peak = float(peaks['bf16_tflops'])
         line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
                             # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, read from the
                             # committed summary of the final build's `ncu --set full` capture (tools/ncu_summary.py
                             # writes profiles/roofline_traffic.json); null when no capture of this build exists
-                            'traffic': roofline_traffic('conv3x3_chain_kernel'),
+                            'traffic': roofline_traffic('cfg2_train_chain'),
                             'kernel': 'conv3x3_chain_kernel<48,48> (forward + backward-data conv layers of the step, persistent data-flow launch)',
                             'launches_timed': len(recs), 'avg_launch_us': float(durs.mean() * 1e6),
-                            'peak_source': peaks_src + ', sustained bf16 (kernel timed inside a long step)'}
+                            'peak_source': peaks_src + ', burst bf16 (kernel timed alone)'}
         line['clocks'] = clocks
         # the same kernel where the problem is large enough for its throughput (not the layer-to-layer hand-over
         # latency) to matter: 16 chained ReLU / residual layers on 8 x 270x480 px, measured live
@@ -504,7 +508,7 @@ def leg_cfg3(dev, timed, engines, peak_burst):
                       'l2': 'back-to-back frames; 64-channel maps at 2x/4x resolution (66 / 265 MB) exceed the L2'},
            'metric': 'sr_x4_output_mpix_per_s', 'unit': 'Mpix/s', 'value': hr_px / sec / 1e6, 'ms_per_frame': sec * 1e3,
            'roofline': {'bound': 'tensor', 'achieved': flops / sec / 1e12, 'peak': peak_burst, 'unit': 'TFLOP/s',
-                        'frac': flops / sec / 1e12 / peak_burst, 'traffic': None,
+                        'frac': flops / sec / 1e12 / peak_burst, 'traffic': None,   # several kernels: see profiles/
                         'kernel': 'whole network: row-marching chain (64->64 body) + conv3x3_tc (64->256 PixelShuffle, 64->3)'},
            'row_path': bool(eng.use_row_path(1, 270, 480))}
     del m, eng
@@ -627,6 +631,7 @@ def steady_state_chain(dev, peak_burst):
     ach = 2.0 * 9 * 48 * 48 * n * h * w * layers / sec / 1e12
     return {'workload': f'{layers} chained 48->48 convs on {n} x {h}x{w} px (activations 100 MB per layer: HBM-resident)',
             'kernel': 'row::conv3x3_row_kernel<48,48> (row-marching, ky-stacked N=144 MMAs; csrc/conv_row.cu)',
+            'traffic_per_layer': (roofline_traffic('steady_state_row_chain') or 0) / 4 or None,
             'achieved': ach, 'peak': peak_burst, 'unit': 'TFLOP/s', 'frac': ach / peak_burst, 'us_per_layer': sec / layers * 1e6,
             'peak_source': 'measured burst bf16 (kernel timed alone)'}
 

@@ -12,6 +12,6 @@ echo "launch list exit $?"
 # skip the two warm-up repetitions' launches: capture the third repetition of every kernel
 ncu --set full --clock-control none --import-source on \
     -k regex:'conv3x3_chain_kernel|conv3x3_row_kernel|wgrad_tc_kernel|wgrad_reduce_kernel|head_bicubic_kernel|head_wgrad|adamw_pack_kernel|conv3x3_tc_kernel' \
-    --launch-skip 0 -c 160 -o gpurun_out/${tag}_step python tools/profile_step.py 1 > gpurun_out/${tag}_ncu_step.log 2>&1
+    --launch-skip 0 -c 48 -o gpurun_out/${tag}_step python tools/profile_step.py 1 > gpurun_out/${tag}_ncu_step.log 2>&1
 echo "full capture exit $?"
 ls -la gpurun_out/${tag}_step.ncu-rep
