@@ -427,12 +427,12 @@ def run_ours(a):
 
     ms_ie = timed(infer_e2e, isteps, warm)
     # same, but the frame leaves the device as the uint8 image get_sr.py / validate.py write and score
-    # (model.upscale_uint8: round/clip on the device, 2.8 MB instead of 11 MB per 720p frame)
+    # (model.upscale_uint8: round/clip in the exit conv's epilogue, 2.8 MB instead of 11 MB per 720p frame)
     host_u8 = torch.empty((1, 3, 4 * INF_H, 4 * INF_W), dtype=torch.uint8).pin_memory()
 
     def infer_e2e_u8(i):
         x = host_frame.to(dev, non_blocking=True)
-        host_u8.copy_(ops.image_to_uint8(model.get_model()(x)), non_blocking=True)
+        host_u8.copy_(eng.forward(x, uint8=True), non_blocking=True)   # uint8 frame from the exit conv's epilogue
         torch.cuda.current_stream().synchronize()
 
     ms_iu = timed(infer_e2e_u8, isteps, warm)

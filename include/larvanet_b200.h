@@ -46,8 +46,9 @@ enum {
   LV_EPI_RGB_NCHW = 3   /* out_hr[n,c,h,w] = post_w[c,:].v[0:3] + post_b[c]   (EDSR final_conv + 1x1)      */
 };
 
-/* packed weight layouts (LV_BF16): tap-major [ntile][src][tap][cin/8][cout][8] (27 MMAs of N=cout per tile) or
- * ky-stacked [src][kx][cin/8][ky*cout_pad+cout][8] (9 MMAs of N=3*cout per tile; cout_pad <= 80, one N tile) */
+/* packed weight layouts (LV_BF16): tap-major [ntile][src][tap][cin/8][cout][8] (27 MMAs of N=cout per 16x8-pixel tile) or
+ * ky-stacked [src][kx][cin/8][ky*cout_pad+cout][8] (row-marching kernel, csrc/conv_row.cu: 9 MMAs of N=3*cout per 128 pixels
+ * of an image row, the three vertical taps summed in TMEM; single-source 48->48 / 64->64 convs only) */
 enum { LV_W_TAP_MAJOR = 0, LV_W_KY_STACKED = 1 };
 
 #define LV_MAX_SRC 4
@@ -87,6 +88,9 @@ typedef struct lv_conv_args {
   void* grad_sign;           /* NHWC [n,h,w,cout] of dtype                                                 */
   const float* post_w;       /* EPI_RGB_NCHW: fp32 [3,3] 1x1 conv weight (row-major [out,in]) or NULL      */
   const float* post_b;       /* EPI_RGB_NCHW: fp32 [3] or NULL                                             */
+  uint8_t* out_u8;           /* EPI_PS4_NCHW: if non-NULL, also store clip(round_half_even(out), 0, 255) as uint8 */
+                             /*   [n,cout/16,4h,4w] -- the PNG-ready frame of get_sr.py:86-89 / validate.py:17-18 --  */
+                             /*   straight from the epilogue (out_hr may then be NULL: no fp32 frame is written)  */
 } lv_conv_args;
 
 /* Weight-gradient work item (one conv layer, or one source slice of the V2 merge conv). */
@@ -143,7 +147,9 @@ int lv_conv3x3_simt(const lv_conv_args* args, void* stream);
  * A chain of convolutions in ONE persistent launch: layers[0..count) are executed in order as if by `count` calls of
  * lv_conv3x3, but the CTAs stay resident and the layers are linked by per-tile data-flow flags instead of kernel
  * boundaries (no launch, prologue or pipeline drain per layer).  Replaces the Conv2d sequences of
- * models/LarvaNet.py:116-140 (ResidualBlock / LarvaBody) and :178-201 (LarvaLeg), forward and input-gradient.
+ * models/LarvaNet.py:205-220 (ResidualBlock), :236-248 (LarvaBody) and :251-267 (LarvaLeg), forward and input-gradient.
+ * Layers with LV_W_TAP_MAJOR weights run on the 16x8-tile data-flow kernel (csrc/conv_chain.cu, 48 channels); layers with
+ * LV_W_KY_STACKED weights on the row-marching kernel (csrc/conv_row.cu, 48 or 64 channels); one layout per call.
  *   layers:  HOST array (copied by value into the launch), 1 <= count <= LV_CHAIN_MAX_LAYERS; every layer must be a single-source
  *            LV_BF16 48 -> 48 conv with LV_W_TAP_MAJOR weights and 16-byte aligned bias, all on the same (n, h, w).
  *            A layer may read (src / res1 / res2 / mask) anything written by an EARLIER layer of the chain or before
@@ -241,19 +247,25 @@ int lv_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * Data-parallel optimizer step (new capability; the reference is single-process): the SUM all-reduce of the
  * gradient arena, optim.AdamW.step() (models/LarvaNet.py:86-88,114) and the operand re-pack of lv_adamw_pack_step in ONE
  * kernel.  Every rank's gradient arena, flag block and loss accumulator live in peer-mapped (symmetric) memory:
- *   peer_grads[r]  fp32 [numel]      gradient arena of rank r as mapped on THIS device (index = rank, own entry included)
- *   peer_flags[r]  uint32 [32]       zero-initialised flag block of rank r (device-side barriers, slot per writer rank)
- *   peer_loss[r]   double [1]        rank r's local loss accumulator; *loss_out (local) receives the sum over ranks
- *   ctl            uint32 [4]        zero-initialised device-LOCAL control words of this rank
- * The kernel waits (device side, over NVLink) until every rank has reached it -- i.e. all gradients are complete --, reads
+ *   peer_grads[r]   fp32 [numel]     gradient arena of rank r as mapped on THIS device (index = rank, own entry included)
+ *   peer_reduced[r] fp32 [world*slice] rank r's buffer of reduced slices, or NULL array: one-shot mode (every rank reads all
+ *                                    arenas; fine for 2 ranks).  Two-shot mode (`slice` = elements per rank, multiple of 4,
+ *                                    world*slice >= numel): rank r reduces slice r into its buffer, a device-side barrier
+ *                                    follows, the update reads each element from its owner -- 2*(world-1)/world arena
+ *                                    reads per rank instead of world-1
+ *   peer_flags[r]   uint32 [48]      zero-initialised flag block of rank r (device-side barriers, slot per writer rank)
+ *   peer_loss[r]    double [1]       rank r's local loss accumulator; *loss_out (local) receives the sum over ranks
+ *   ctl             uint32 [8]       zero-initialised device-LOCAL control words of this rank
+ * The kernel waits (device side, over NVLink) until every rank has reached it -- i.e. all gradients are complete --, sums
  * the gradients of all ranks in rank order (bit-identical sums on every rank), and returns only when every rank is done
  * reading, so the caller may overwrite its arena right after.  Every rank must call it the same number of times.
  * world must be 2, 4 or 8; `host` arrays are read during the call only.
  */
 int lv_dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs, int nconv,
-                          const void* const* peer_grads, void* const* peer_flags, const void* const* peer_loss,
-                          double* loss_out, uint32_t* ctl, int world, int rank, void* stream);
+                          const void* const* peer_grads, void* const* peer_reduced, void* const* peer_flags,
+                          const void* const* peer_loss, double* loss_out, uint32_t* ctl, int64_t slice, int world, int rank,
+                          void* stream);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t lv_launch_count(void);

@@ -35,7 +35,7 @@ class ConvArgs(C.Structure):
         ('res1', C.c_void_p), ('res2', C.c_void_p), ('out', C.c_void_p),
         ('out_hr', C.c_void_p), ('base_hr', C.c_void_p), ('truth_hr', C.c_void_p),
         ('loss_sum', C.c_void_p), ('grad_sign', C.c_void_p),
-        ('post_w', C.c_void_p), ('post_b', C.c_void_p),
+        ('post_w', C.c_void_p), ('post_b', C.c_void_p), ('out_u8', C.c_void_p),
     ]
 
 
@@ -91,7 +91,7 @@ SIGNATURES = {
     'lv_adamw_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_void_p]),
     'lv_dp_adamw_pack_step': (C.c_int, [C.c_void_p] * 3 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float,
                                                                                          C.POINTER(FusedConv), C.c_int] +
-                              [C.POINTER(C.c_void_p)] * 3 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+                              [C.POINTER(C.c_void_p)] * 4 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     'lv_launch_count': (C.c_int64, []),
 }
 

@@ -64,7 +64,8 @@ int adamw_pack_step(float*, const float*, float*, float*, long long, float, floa
                     const lv_fused_conv*, int, cudaStream_t);
 int psnr_sqsum(const float*, const float*, double*, int, int, int, int, int, cudaStream_t);
 int dp_adamw_pack_step(float*, float*, float*, long long, float, float, float, float, float, int, float, const lv_fused_conv*, int,
-                       const void* const*, void* const*, const void* const*, double*, uint32_t*, int, int, cudaStream_t);
+                       const void* const*, void* const*, void* const*, const void* const*, double*, uint32_t*, long long, int, int,
+                       cudaStream_t);
 long long wgrad_workspace_bytes(const lv_wgrad_item*, int, int);
 int wgrad(const lv_wgrad_item*, const lv_wgrad_item*, int, int, void*, cudaStream_t);
 int wgrad_simt(const lv_wgrad_item*, const lv_wgrad_item*, int, int, cudaStream_t);
@@ -85,7 +86,8 @@ static int check_conv(const lv_conv_args* a) {
       break;
     case LV_EPI_PS4_NCHW:
       LV_CHECK_ARG(a->cout % 16 == 0, "conv3x3: EPI_PS4 needs cout %% 16 == 0");
-      LV_CHECK_ARG(a->out_hr != nullptr || a->truth_hr != nullptr, "conv3x3: EPI_PS4 needs out_hr and/or truth_hr");
+      LV_CHECK_ARG(a->out_hr != nullptr || a->truth_hr != nullptr || a->out_u8 != nullptr,
+                   "conv3x3: EPI_PS4 needs out_hr, out_u8 and/or truth_hr");
       LV_CHECK_ARG(a->truth_hr == nullptr || a->loss_sum != nullptr, "conv3x3: truth_hr given without loss_sum");
       break;
     case LV_EPI_PS2_NHWC:
@@ -251,11 +253,12 @@ int lv_adamw_pack_step(float* param, const float* grad, float* exp_avg, float* e
 
 int lv_dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr, float beta1, float beta2,
                           float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs, int nconv,
-                          const void* const* peer_grads, void* const* peer_flags, const void* const* peer_loss,
-                          double* loss_out, uint32_t* ctl, int world, int rank, void* stream) {
+                          const void* const* peer_grads, void* const* peer_reduced, void* const* peer_flags,
+                          const void* const* peer_loss, double* loss_out, uint32_t* ctl, int64_t slice, int world, int rank,
+                          void* stream) {
   LV_CHECK_ARG(param && exp_avg && exp_avg_sq, "dp adamw+pack: null pointer");
   return dp_adamw_pack_step(param, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, grad_scale, convs,
-                            nconv, peer_grads, peer_flags, peer_loss, loss_out, ctl, world, rank,
+                            nconv, peer_grads, peer_reduced, peer_flags, peer_loss, loss_out, ctl, slice, world, rank,
                             static_cast<cudaStream_t>(stream));
 }
 

@@ -175,6 +175,7 @@ __device__ __forceinline__ float ps4_tile(const lv_conv_args& a, const float* bi
         float4 o = make_float4(v[4 * i] + bb.x, v[4 * i + 1] + bb.y, v[4 * i + 2] + bb.z, v[4 * i + 3] + bb.w);
         if (has_base) { o.x += qb[i].x; o.y += qb[i].y; o.z += qb[i].z; o.w += qb[i].w; }
         if (has_out) *reinterpret_cast<float4*>(a.out_hr + hr0 + c * plane + i * W4) = o;
+        if (a.out_u8 != nullptr) *reinterpret_cast<uint32_t*>(a.out_u8 + hr0 + c * plane + i * W4) = pack_u8x4(o);
         if (has_truth) {
           const float d0 = o.x - qt[i].x, d1 = o.y - qt[i].y, d2 = o.z - qt[i].z, d3 = o.w - qt[i].w;
           closs += fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);

@@ -79,6 +79,7 @@ __device__ __forceinline__ float conv_epilogue16(const lv_conv_args& a, int n, i
         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
       }
       if (a.out_hr != nullptr) *reinterpret_cast<float4*>(a.out_hr + off) = o;
+      if (a.out_u8 != nullptr) *reinterpret_cast<uint32_t*>(a.out_u8 + off) = pack_u8x4(o);
       if (a.truth_hr != nullptr) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(a.truth_hr + off));
         const float d0 = o.x - t.x, d1 = o.y - t.y, d2 = o.z - t.z, d3 = o.w - t.w;

@@ -328,13 +328,21 @@ struct FusedBatch {
 // the peers' HBM over NVLink (symmetric / peer-mapped memory), in rank order on every rank -- so every rank computes the
 // bit-identical sum and the replicas' weights never drift apart.  One kernel = device-side barrier ("every rank's
 // gradients are complete") + all-reduce + AdamW + operand re-pack + device-side barrier ("every rank is done reading").
-constexpr int kDpMaxRanks = 16, kDpFlagWords = 2 * kDpMaxRanks;
+// Two ways to read the sum (template TWO):
+//   one-shot (world 2): every rank reads all ranks' arenas -- (world-1) x 3.3 MB over NVLink, one barrier pair;
+//   two-shot (world >= 4; at 8 ranks the one-shot read is 23 MB = 30 us): rank r first reduces ITS 1/world slice from all
+//     peers into its `reduced` buffer, a second device-side barrier follows, and the update then reads every element
+//     from its owner's reduced buffer -- 2 x (world-1)/world x 3.3 MB per rank.
+constexpr int kDpMaxRanks = 16;
 struct DpCtx {
   const float* grad[kDpMaxRanks];     // gradient arena of rank r (peer-mapped address on this device)
-  uint32_t* flags[kDpMaxRanks];       // flag block of rank r: [start barrier: slot per writer rank][end barrier: same]
+  float* reduced[kDpMaxRanks];        // two-shot: rank r's buffer of reduced slices (only slice r is ever written by r)
+  uint32_t* flags[kDpMaxRanks];       // flag block of rank r: three barriers x one slot per writer rank (start, end, middle)
   const double* loss[kDpMaxRanks];    // local loss accumulator of rank r
   double* loss_out;                   // this rank: sum over ranks
-  uint32_t* ctl;                      // this rank, device-local control words: [0] epoch, [1] go, [2] blocks arrived
+  uint32_t* ctl;                      // this rank, device-local control words: [0] epoch, [1] go, [2] blocks arrived (end),
+                                      // [3] blocks arrived (middle), [4] go (middle)
+  long long slice;                    // two-shot: elements per rank's slice (multiple of 4; world * slice >= numel)
   int world, rank;
 };
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -367,10 +375,20 @@ __device__ __forceinline__ void spin_until_sys(const uint32_t* p, uint32_t need)
   }
 }
 
-template <int NP>
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+template <int NP, bool TWO>
 __device__ __forceinline__ float grad_at(const float* g, const DpCtx& dp, long long i) {
   if constexpr (NP == 0) {
     return g[i];
+  } else if constexpr (TWO) {
+    // the element's owner reduced it in phase A
+    const unsigned owner = static_cast<unsigned>(i) / static_cast<unsigned>(dp.slice);
+    return ld_peer_f32(dp.reduced[owner] + i);
   } else {
     float part[NP];
 #pragma unroll
@@ -382,10 +400,10 @@ __device__ __forceinline__ float grad_at(const float* g, const DpCtx& dp, long l
   }
 }
 
-template <int NP>
+template <int NP, bool TWO>
 __device__ __forceinline__ float adamw_one(float* p, const float* g, const DpCtx& dp, float* m, float* v, long long i, float lr,
                                            float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
-  const float grad = grad_at<NP>(g, dp, i) * gscale;
+  const float grad = grad_at<NP, TWO>(g, dp, i) * gscale;
   float pv = p[i] * (1.f - lr * wd);
   const float mv = m[i] + (grad - m[i]) * (1.f - b1);            // lerp_, as torch does
   const float vv = v[i] * b2 + (1.f - b2) * grad * grad;
@@ -393,6 +411,52 @@ __device__ __forceinline__ float adamw_one(float* p, const float* g, const DpCtx
   pv -= (lr / bc1) * (mv / denom);
   p[i] = pv; m[i] = mv; v[i] = vv;
   return pv;
+}
+
+// two-shot phase A + middle barrier: this rank's slice of the sum, then "every rank's slice is reduced and visible"
+template <int NP>
+__device__ __forceinline__ void dp_reduce_slice(const DpCtx& dp, uint32_t e) {
+  __shared__ uint32_t s_last_mid;
+  const int t = threadIdx.x;
+  const long long base = static_cast<long long>(dp.rank) * dp.slice;
+  const long long n4 = dp.slice / 4;
+  float* dst = dp.reduced[dp.rank] + base;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + t; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 part[NP];
+#pragma unroll
+    for (int r = 0; r < NP; ++r) part[r] = ld_peer_v4(dp.grad[r] + base + 4 * i);
+    float4 s = part[0];
+#pragma unroll
+    for (int r = 1; r < NP; ++r) { s.x += part[r].x; s.y += part[r].y; s.z += part[r].z; s.w += part[r].w; }   // rank order: identical sums
+    *reinterpret_cast<float4*>(dst + 4 * i) = s;
+  }
+  // grid barrier (every block of this rank is resident: grid <= co-resident blocks, checked on the host), then the
+  // cross-rank barrier by the last block to arrive, then release the grid
+  __syncthreads();
+  if (t == 0) {
+    __threadfence_system();
+    const uint32_t prev = atomicAdd(dp.ctl + 3, 1u);
+    s_last_mid = (prev == gridDim.x - 1u) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last_mid != 0u) {
+    if (t < NP) {
+      st_release_sys(dp.flags[t] + 2 * kDpMaxRanks + dp.rank, e);
+      spin_until_sys(dp.flags[dp.rank] + 2 * kDpMaxRanks + t, e);
+    }
+    __syncthreads();
+    if (t == 0) {
+      dp.ctl[3] = 0u;
+      st_release_gpu(dp.ctl + 4, e);
+    }
+  } else if (t == 0) {
+    uint32_t spins = 0;
+    while (ld_acquire_gpu_u32(dp.ctl + 4) < e) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) asm volatile("trap;");
+    }
+  }
+  __syncthreads();
 }
 
 // entry barrier of the data-parallel kernel; returns this launch's epoch
@@ -454,7 +518,7 @@ __device__ __forceinline__ void dp_leave(const DpCtx& dp, uint32_t e) {
   }
 }
 
-template <int NP>
+template <int NP, bool TWO>
 __global__ void __launch_bounds__(192)
 adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   const __grid_constant__ FusedBatch fb, const __grid_constant__ DpCtx dp, float lr, float b1, float b2,
@@ -463,11 +527,12 @@ adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
   const int t = threadIdx.x;
   uint32_t epoch = 0;
   if constexpr (NP > 0) epoch = dp_enter<NP>(dp);
+  if constexpr (TWO) dp_reduce_slice<NP>(dp, epoch);
   if (static_cast<int>(blockIdx.x) >= fb.brick_blocks) {   // biases, head conv, anything without a packed operand
     const int row = (static_cast<int>(blockIdx.x) - fb.brick_blocks) * kFusedRowsPerBlock + t / kFusedRow;
     const int i = t % kFusedRow;
     if (row < fb.nrows && i < fb.row_cnt[row])
-      adamw_one<NP>(p, g, dp, m, v, fb.row_off[row] + i, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      adamw_one<NP, TWO>(p, g, dp, m, v, fb.row_off[row] + i, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
     if constexpr (NP > 0) dp_leave<NP>(dp, epoch);
     return;
   }
@@ -484,7 +549,7 @@ adamw_pack_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
       const int e = t + 192 * r;                 // 0..575
       const int oo = e / 72, rem = e - oo * 72;  // rem = ii*9 + tap: 72 contiguous floats of output channel 8*ob+oo
       const long long idx = cv.w_off + (static_cast<long long>(8 * ob + oo) * cv.I + 8 * ib) * 9 + rem;
-      sm[oo][rem] = adamw_one<NP>(p, g, dp, m, v, idx, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
+      sm[oo][rem] = adamw_one<NP, TWO>(p, g, dp, m, v, idx, lr, b1, b2, eps, wd, bc1, bc2_sqrt, gscale);
     }
     __syncthreads();
     const int s = ib / 6, chunk = ib - 6 * s;    // source slice and 8-channel chunk of the brick's input channels
@@ -564,7 +629,7 @@ int adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   const int tail_blocks = (fb.nrows + kFusedRowsPerBlock - 1) / kFusedRowsPerBlock;
-  adamw_pack_kernel<0><<<fb.brick_blocks + tail_blocks, 192, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, fb, none, lr, beta1, beta2,
+  adamw_pack_kernel<0, false><<<fb.brick_blocks + tail_blocks, 192, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, fb, none, lr, beta1, beta2,
                                                                        eps, weight_decay, static_cast<float>(bc1),
                                                                        static_cast<float>(sqrt(bc2)), grad_scale);
   LV_LAUNCH_OK();
@@ -574,44 +639,55 @@ int adamw_pack_step(float* param, const float* grad, float* exp_avg, float* exp_
 // Data-parallel optimizer step: gradient all-reduce over peer memory + AdamW + operand re-pack in ONE kernel (see DpCtx).
 int dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, long long numel, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, float grad_scale, const lv_fused_conv* convs, int nconv,
-                       const void* const* peer_grads, void* const* peer_flags, const void* const* peer_loss, double* loss_out,
-                       uint32_t* ctl, int world, int rank, cudaStream_t stream) {
+                       const void* const* peer_grads, void* const* peer_reduced, void* const* peer_flags,
+                       const void* const* peer_loss, double* loss_out, uint32_t* ctl, long long slice, int world, int rank,
+                       cudaStream_t stream) {
   if (numel == 0) return LV_OK;
   LV_CHECK_ARG(step >= 1, "adamw: step must be >= 1");
   LV_CHECK_ARG(world == 2 || world == 4 || world == 8, "dp adamw: world size must be 2, 4 or 8 (got %d)", world);
   LV_CHECK_ARG(rank >= 0 && rank < world, "dp adamw: rank %d outside 0..%d", rank, world - 1);
   LV_CHECK_ARG(peer_grads && peer_flags && peer_loss && loss_out && ctl, "dp adamw: null pointer");
+  const bool two = peer_reduced != nullptr && slice > 0;
+  if (two) LV_CHECK_ARG(slice % 4 == 0 && slice * world >= numel && numel < (1ll << 31), "dp adamw: bad slice %lld", slice);
   static thread_local FusedBatch fb;
   static thread_local DpCtx dp;
   int rc = build_fused_batch(fb, numel, convs, nconv);
   if (rc != LV_OK) return rc;
   for (int r = 0; r < world; ++r) {
-    LV_CHECK_ARG(peer_grads[r] && peer_flags[r] && peer_loss[r], "dp adamw: null pointer for rank %d", r);
+    LV_CHECK_ARG(peer_grads[r] && peer_flags[r] && peer_loss[r] && (!two || peer_reduced[r]), "dp adamw: null pointer for rank %d", r);
     dp.grad[r] = static_cast<const float*>(peer_grads[r]);
+    dp.reduced[r] = two ? static_cast<float*>(peer_reduced[r]) : nullptr;
     dp.flags[r] = static_cast<uint32_t*>(peer_flags[r]);
     dp.loss[r] = static_cast<const double*>(peer_loss[r]);
   }
   dp.loss_out = loss_out;
   dp.ctl = ctl;
+  dp.slice = slice;
   dp.world = world;
   dp.rank = rank;
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  if (two) {
+    // the middle barrier is a grid barrier: every block must be resident at once (192 threads, ~56 registers: at least 4
+    // blocks per SM)
+    const int cap = 4 * sm_count();
+    if (fb.brick_blocks > cap - 64) fb.brick_blocks = cap - 64;
+  }
   const int tail_blocks = (fb.nrows + kFusedRowsPerBlock - 1) / kFusedRowsPerBlock;
   const int grid = fb.brick_blocks + tail_blocks;
+  if (two) LV_CHECK_ARG(grid <= 4 * sm_count(), "dp adamw: %d blocks cannot be co-resident", grid);
   const float* g = dp.grad[rank];
-#define LV_DP_CASE(NPV)                                                                                                   \
-  case NPV:                                                                                                               \
-    adamw_pack_kernel<NPV><<<grid, 192, 0, stream>>>(param, g, exp_avg, exp_avg_sq, fb, dp, lr, beta1, beta2, eps,         \
-                                                     weight_decay, static_cast<float>(bc1), static_cast<float>(sqrt(bc2)), \
-                                                     grad_scale);                                                         \
-    break;
-  switch (world) {
-    LV_DP_CASE(2)
-    LV_DP_CASE(4)
-    LV_DP_CASE(8)
-  }
-#undef LV_DP_CASE
+#define LV_DP_LAUNCH(NPV, TWOV)                                                                                           \
+  adamw_pack_kernel<NPV, TWOV><<<grid, 192, 0, stream>>>(param, g, exp_avg, exp_avg_sq, fb, dp, lr, beta1, beta2, eps,     \
+                                                         weight_decay, static_cast<float>(bc1),                           \
+                                                         static_cast<float>(sqrt(bc2)), grad_scale)
+  if (world == 2 && !two) LV_DP_LAUNCH(2, false);
+  else if (world == 2) LV_DP_LAUNCH(2, true);
+  else if (world == 4 && !two) LV_DP_LAUNCH(4, false);
+  else if (world == 4) LV_DP_LAUNCH(4, true);
+  else if (world == 8 && !two) LV_DP_LAUNCH(8, false);
+  else LV_DP_LAUNCH(8, true);
+#undef LV_DP_LAUNCH
   LV_LAUNCH_OK();
   return LV_OK;
 }

@@ -160,6 +160,15 @@ __device__ __forceinline__ void store16_act(T* base, int n, int y, int x, int co
   }
 }
 
+// clip(round_half_even(v), 0, 255) of four fp32 samples packed into one 32-bit word (little endian: x first), the same
+// arithmetic as lv_image_to_uint8 / validate._image_to_uint8 (np.round rounds half to even)
+__device__ __forceinline__ uint32_t pack_u8x4(float4 v) {
+  const int a = min(max(__float2int_rn(v.x), 0), 255), b = min(max(__float2int_rn(v.y), 0), 255);
+  const int c = min(max(__float2int_rn(v.z), 0), 255), d = min(max(__float2int_rn(v.w), 0), 255);
+  return static_cast<uint32_t>(a) | (static_cast<uint32_t>(b) << 8) | (static_cast<uint32_t>(c) << 16) |
+         (static_cast<uint32_t>(d) << 24);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

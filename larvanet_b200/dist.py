@@ -61,7 +61,7 @@ class SymmetricGradExchange:
     Construction is collective.  Every rank reports success or failure and the group only switches over if ALL ranks
     succeeded; otherwise everybody keeps the NCCL all-reduce (`allreduce_gradients`)."""
 
-    TAIL = 64   # floats behind the gradient arena: [0:2] this rank's loss (one double), [16:48] device-barrier flags
+    TAIL = 96   # floats behind the gradient arena: [0:2] this rank's loss (one double), [16:64] device-barrier flags
 
     def __init__(self, numel, device, group=None):
         """Local half of the construction (no collective): allocate this rank's symmetric buffer."""
@@ -72,7 +72,8 @@ class SymmetricGradExchange:
         self.rank = dist.get_rank(self.group)
         pad = 4 * 32 * self.world                  # 16-byte vectors x 32 lanes x ranks: keeps every rank's share aligned
         self.numel = (int(numel) + pad - 1) // pad * pad
-        self.storage = symm_mem.empty(self.numel + self.TAIL, dtype=torch.float32, device=device)
+        # [gradient arena | tail | reduced slices (two-shot exchange: rank r writes slice r of its copy)]
+        self.storage = symm_mem.empty(2 * self.numel + self.TAIL, dtype=torch.float32, device=device)
         self.storage.zero_()
         self.buffer = self.storage[:self.numel]    # the gradient arena the engine writes into
         self.loss_view = self.storage[self.numel:self.numel + 2].view(torch.float64)   # this rank's loss accumulator
@@ -146,8 +147,13 @@ class PeerArena:
         self.grad_ptrs = (C.c_void_p * self.world)(*bases)
         self.loss_ptrs = (C.c_void_p * self.world)(*[b + n * 4 for b in bases])
         self.flag_ptrs = (C.c_void_p * self.world)(*[b + (n + 16) * 4 for b in bases])
+        self.reduced_ptrs = (C.c_void_p * self.world)(*[b + (n + ex.TAIL) * 4 for b in bases])
+        self.slice = n // self.world                      # numel is padded to a multiple of 128 * world
+        # two-shot from 4 ranks on (one-shot at 8 ranks reads 7 x 3.3 MB per rank: ~30 us); LARVANET_B200_DP_TWO_SHOT=0/1 forces
+        mode = os.environ.get('LARVANET_B200_DP_TWO_SHOT', 'auto')
+        self.two_shot = (self.world >= 4) if mode == 'auto' else mode == '1'
         self.loss_out = torch.zeros(1, dtype=torch.float64, device=ex.storage.device)   # sum over ranks, written by the kernel
-        self.ctl = torch.zeros(4, dtype=torch.int32, device=ex.storage.device)
+        self.ctl = torch.zeros(8, dtype=torch.int32, device=ex.storage.device)
         self.supported = self.world in (2, 4, 8)
 
 

@@ -394,15 +394,21 @@ class LarvaEngine:
         b.u = self._act(n, h, w)
         b.mf = self._act(n, h, w) if self.v2 else None
         b.row = self.use_row_path(n, h, w)
+        b.out_u8 = None
         return b
 
-    def _run_infer(self, b, exit_leg=None):
+    def _run_infer(self, b, exit_leg=None, u8=False):
+        """`u8`: the exit conv's epilogue writes the uint8 frame (round + clip) INSTEAD of the fp32 one."""
         self._row_active = b.row
+        outs = dict(out_u8=b.out_u8) if u8 else dict(out_hr=b.out)
         hw, hb = self._w('head.feature_extraction')
         k = self.m if exit_leg is None else exit_leg
         ops.head_bicubic(b.x, hw, hb, b.f0, b.base)
         if k == 0:
-            b.out.copy_(b.base)
+            if u8:
+                ops.image_to_uint8(b.base, b.out_u8)
+            else:
+                b.out.copy_(b.base)
             return
         self._begin_chain()
         fin = b.f0
@@ -422,29 +428,33 @@ class LarvaEngine:
         if self.v2 and exit_leg is None:
             self._conv(b.feats, 'tail.merge_conv', out=b.mf)
             self._conv([b.mf], 'tail.recon_block.0', out=b.u, relu=True)
-            self._conv([b.u], 'tail.recon_block.2', epilogue=LV_EPI_PS4_NCHW, out_hr=b.out, base_hr=b.base)
+            self._conv([b.u], 'tail.recon_block.2', epilogue=LV_EPI_PS4_NCHW, base_hr=b.base, **outs)
         else:
             p = f'body_{k - 1}.leg.recon_block'
             self._conv([fin], p + '.0', out=b.u, relu=True)
-            self._conv([b.u], p + '.2', epilogue=LV_EPI_PS4_NCHW, out_hr=b.out, base_hr=b.base)
+            self._conv([b.u], p + '.2', epilogue=LV_EPI_PS4_NCHW, base_hr=b.base, **outs)
         self._flush_chain(end=True)
 
-    def forward(self, x, exit_leg=None):
-        """x: fp32 NCHW [n,3,h,w] CUDA tensor on the 0..255 scale -> fp32 NCHW [n,3,4h,4w] (engine-owned buffer)."""
+    def forward(self, x, exit_leg=None, uint8=False):
+        """x: fp32 NCHW [n,3,h,w] CUDA tensor on the 0..255 scale -> fp32 NCHW [n,3,4h,4w] (engine-owned buffer), or, with
+        `uint8`, the PNG-ready uint8 frame clip(round(.)) written straight from the exit conv's epilogue (reference
+        get_sr.py:86-89, validate.py:17-18): no fp32 frame is stored and no conversion kernel runs."""
         if x.dim() != 4 or x.shape[1] != 3:
             raise LarvaNetB200Error(f'expected NCHW input with 3 channels, got {tuple(x.shape)}')
         n, _, h, w = (int(v) for v in x.shape)
         self.repack(backward=False)
-        key = (n, h, w, exit_leg)
+        key = (n, h, w, exit_leg, bool(uint8))
         ent = self._infer.get(key, lambda: self._build_infer(n, h, w))
         b = ent['bufs']
+        if uint8 and b.out_u8 is None:
+            b.out_u8 = torch.empty((n, 3, 4 * h, 4 * w), dtype=torch.uint8, device=self.device)
         if b.row:
             self.repack_ky(backward=False)
         b.x.copy_(x.to(dtype=torch.float32), non_blocking=True)
         if n * h * w == 0:
-            return b.out
-        _run_cached(self, ent, lambda: self._run_infer(b, exit_leg))
-        return b.out
+            return b.out_u8 if uint8 else b.out
+        _run_cached(self, ent, lambda: self._run_infer(b, exit_leg, uint8))
+        return b.out_u8 if uint8 else b.out
 
     # ------------------------------------------------------------------ training
     def _build_train(self, n, h, w):

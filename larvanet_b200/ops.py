@@ -105,7 +105,7 @@ def pack_weights(items):
 
 def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res1=None, res2=None, out=None,
                    epilogue=LV_EPI_NHWC, out_hr=None, base_hr=None, truth_hr=None, loss_sum=None, grad_sign=None,
-                   post_w=None, post_b=None, res_scale=1.0, wlayout=0):
+                   post_w=None, post_b=None, res_scale=1.0, wlayout=0, out_u8=None):
     """Build an lv_conv_args from torch tensors.  srcs: list of planar-8 activation tensors (same shape/dtype)."""
     x0 = srcs[0]
     dt = x0.dtype
@@ -134,6 +134,7 @@ def make_conv_args(srcs, weights, cout, *, bias=None, relu=False, mask=None, res
     a.grad_sign = _ptr(grad_sign, dt, 'grad_sign')
     a.post_w = _ptr(post_w, torch.float32, 'post_w')
     a.post_b = _ptr(post_b, torch.float32, 'post_b')
+    a.out_u8 = _ptr(out_u8, torch.uint8, 'out_u8')
     return a
 
 
@@ -347,8 +348,9 @@ def dp_adamw_pack_step(param, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight
     check(_lib.load().lv_dp_adamw_pack_step(
         _ptr(param, torch.float32, 'param'), _ptr(exp_avg, torch.float32, 'exp_avg'), _ptr(exp_avg_sq, torch.float32, 'exp_avg_sq'),
         param.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), float(grad_scale),
-        arr, cnt, peers.grad_ptrs, peers.flag_ptrs, peers.loss_ptrs, peers.loss_out.data_ptr(), peers.ctl.data_ptr(),
-        int(peers.world), int(peers.rank), _stream()), 'lv_dp_adamw_pack_step')
+        arr, cnt, peers.grad_ptrs, peers.reduced_ptrs if peers.two_shot else None, peers.flag_ptrs, peers.loss_ptrs,
+        peers.loss_out.data_ptr(), peers.ctl.data_ptr(), int(peers.slice) if peers.two_shot else 0, int(peers.world),
+        int(peers.rank), _stream()), 'lv_dp_adamw_pack_step')
 
 
 def adamw_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):

@@ -331,10 +331,10 @@ class LarvaNet(BaseModel):
 
     def upscale_uint8(self, input_list, scale):
         """`validate._image_to_uint8(self.upscale(...))` with the round/clip done on the device: the device->host copy
-        is 1 byte per sample instead of 4 (what get_sr.py / validate.py need before they write or score a PNG)."""
-        from larvanet_b200 import ops
-        out = self.model(self._as_input(input_list))
-        return ops.image_to_uint8(out.contiguous()).cpu().numpy()
+        is 1 byte per sample instead of 4 (what get_sr.py / validate.py need before they write or score a PNG).  The uint8
+        frame comes straight out of the exit conv's PixelShuffle epilogue (`lv_conv_args.out_u8`): no fp32 frame is written."""
+        m = self.model
+        return m.engine().forward(self._as_input(input_list), exit_leg=m.leg, uint8=True).cpu().numpy()
 
     def test(self, input_list):
         return self.model(self._as_input(input_list))

@@ -34,10 +34,18 @@ def _torchrun(nproc, args, timeout=600, env_extra=None):
 
 
 @needs2
-@pytest.mark.parametrize('symm', ['1', '0'], ids=['peer_memory_exchange', 'nccl_allreduce'])
-def test_dp_gradients_equal_single_process(symm):
-    out = _torchrun(2, ['tools/dp_check.py'], env_extra={'LARVANET_B200_SYMM_ALLREDUCE': symm})
+@pytest.mark.parametrize('symm,two_shot', [('1', '0'), ('1', '1'), ('0', '0')],
+                         ids=['peer_memory_one_shot', 'peer_memory_two_shot', 'nccl_allreduce'])
+def test_dp_gradients_equal_single_process(symm, two_shot):
+    """tools/dp_check.py: gradients of 2 ranks x half the batch == one process on the whole batch (also uneven shards), and
+    four optimizer steps through the fused exchange + AdamW + re-pack kernel (one-shot and two-shot forms) track a single
+    process and leave bit-identical replicas."""
+    out = _torchrun(2, ['tools/dp_check.py'], env_extra={'LARVANET_B200_SYMM_ALLREDUCE': symm,
+                                                          'LARVANET_B200_DP_TWO_SHOT': two_shot})
     assert out.count('rel grad diff') == 3, out
+    assert 'replicas bit-identical: True' in out, out
+    if symm == '1':
+        assert 'fused=True' in out, out
 
 
 @needs2

@@ -206,6 +206,40 @@ def test_leg_plugins_match_reference_golden(golden_dir, name, precision):
             assert np.max(np.abs(out - ref)) <= 2.0
 
 
+@pytest.mark.parametrize('precision', ['bf16', 'fp32'])
+def test_tile_sharded_inference_is_exact(precision):
+    """Bands with a receptive-field halo (larvanet_b200/tiling.py), upscaled independently and stitched on the device, equal
+    the full-frame result BIT FOR BIT -- unlike the reference's chop-forward, whose 10-pixel overlap is inexact
+    (utils/image_utils.py:7-66).  Also the uint8 variant and the per-rank band split of a multi-GPU run."""
+    from larvanet_b200 import tiling
+    blocks = [2, 2]
+    params = synth.make_larva_params(blocks, seed=8, bias_std=0.02)
+    lr, _ = synth.make_images(1, 97, 61, seed=9)
+    m = _make(False, blocks, precision)
+    load_params(m.get_model(), params)
+    eng = m._engine()
+    x = torch.from_numpy(lr).cuda()
+    full = eng.forward(x).clone()
+    halo = tiling.receptive_halo(blocks)
+    assert halo == 1 + 2 * 4 + 2 + 2
+    for bands in (2, 3, 5):
+        got = tiling.upscale_banded(eng, x, bands)
+        assert torch.equal(got, full), f'{bands} bands differ from the full frame'
+    # a halo one ring too small is NOT exact (the test would be vacuous otherwise)
+    small = tiling.upscale_banded(eng, x, 3, halo=halo - 4)
+    assert not torch.equal(small, full)
+    # uint8 frames and a 2-rank split (each rank computes its own bands; together they cover the frame)
+    full_u8 = eng.forward(x, uint8=True).clone()
+    parts = [tiling.upscale_banded(eng, x, 4, uint8=True, only=tiling.bands_for_rank(4, r, 2)) for r in range(2)]
+    for b, (y0, y1, _, _) in enumerate(tiling.band_ranges(97, 4, halo)):
+        owner = b % 2
+        assert torch.equal(parts[owner][:, :, 4 * y0:4 * y1], full_u8[:, :, 4 * y0:4 * y1])
+    # the reference's chop-forward on the same frame is visibly inexact at its default overlap
+    from utils import image_utils
+    chop = image_utils.upscale_with_chop_forward(m, lr[0], scale=4, overlap_size=20)
+    assert np.max(np.abs(chop - full.cpu().numpy()[0])) > 0.0
+
+
 @pytest.mark.parametrize('shape', [(1, 180, 320), (4, 48, 48)])
 def test_tensor_core_path_equals_cuda_core_path_at_full_size(shape):
     """BASELINE config sizes: the tcgen05 chain vs the CUDA-core chain on identical bf16 operands (size-independent

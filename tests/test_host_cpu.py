@@ -28,8 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_struct_layout_matches_header_sizes():
     import ctypes as C
-    # 12 x 4-byte scalars, then 17 pointers (4 sources + 13 others)
-    assert C.sizeof(_lib.ConvArgs) == 12 * 4 + 17 * 8
+    # 12 x 4-byte scalars, then 18 pointers (4 sources + 14 others)
+    assert C.sizeof(_lib.ConvArgs) == 12 * 4 + 18 * 8
     assert C.sizeof(_lib.WgradItem) == 8 * 4 + 4 * 8 + 8
     assert C.sizeof(_lib.PackItem) == 2 * 8 + 8 * 4
 
