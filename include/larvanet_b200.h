@@ -267,6 +267,24 @@ int lv_dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, int64
                           const void* const* peer_loss, double* loss_out, uint32_t* ctl, int64_t slice, int world, int rank,
                           void* stream);
 
+/*
+ * Device-side training-patch pipeline: random crop + rot90 + horizontal flip of HBM-resident LR / HR image pairs, written
+ * straight into the step's batch tensors -- replaces the host-side numpy pipeline of dataloaders/div2k_train_loader.py:72-98
+ * (and the torch-op variant dataloaders/div2k_train_loader_tensor.py:57-97) plus the per-step host->device copy of
+ * train_larva.py:123-124.  `items_dev`: DEVICE array of `count` items (one per patch; the random draws are the caller's):
+ *   out_lr[b] = flip?( rot90( lr[:, y:y+patch, x:x+patch], rot ) ),  out_hr[b] likewise at `scale` times the coordinates
+ * (rot = number of counter-clockwise quarter turns as in torch.rot90(k, dims=(1,2)); flip reverses the last axis).
+ */
+typedef struct lv_patch_item {
+  const float* lr;           /* fp32 [3, h, w], 0..255                       */
+  const float* hr;           /* fp32 [3, scale*h, scale*w]                   */
+  int32_t h, w;              /* LR image size                                */
+  int32_t y, x;              /* LR crop origin (0 <= y <= h-patch, same for x) */
+  int32_t rot, flip;
+} lv_patch_item;
+int lv_crop_augment(const lv_patch_item* items_dev, int count, float* out_lr, float* out_hr, int patch, int scale,
+                    void* stream);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t lv_launch_count(void);
 

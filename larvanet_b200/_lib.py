@@ -54,6 +54,11 @@ class FusedConv(C.Structure):
                 ('bwd', C.c_void_p * LV_MAX_SRC)]
 
 
+class PatchItem(C.Structure):
+    _fields_ = [('lr', C.c_void_p), ('hr', C.c_void_p), ('h', C.c_int32), ('w', C.c_int32), ('y', C.c_int32), ('x', C.c_int32),
+                ('rot', C.c_int32), ('flip', C.c_int32)]
+
+
 class PackItem(C.Structure):
     _fields_ = [
         ('w', C.c_void_p), ('packed', C.c_void_p),
@@ -92,6 +97,7 @@ SIGNATURES = {
     'lv_dp_adamw_pack_step': (C.c_int, [C.c_void_p] * 3 + [C.c_int64] + [C.c_float] * 5 + [C.c_int, C.c_float,
                                                                                          C.POINTER(FusedConv), C.c_int] +
                               [C.POINTER(C.c_void_p)] * 4 + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    'lv_crop_augment': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'lv_launch_count': (C.c_int64, []),
 }
 

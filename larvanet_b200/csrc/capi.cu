@@ -63,6 +63,7 @@ int image_to_uint8(const float*, uint8_t*, long long, cudaStream_t);
 int adamw_pack_step(float*, const float*, float*, float*, long long, float, float, float, float, float, int, float,
                     const lv_fused_conv*, int, cudaStream_t);
 int psnr_sqsum(const float*, const float*, double*, int, int, int, int, int, cudaStream_t);
+int crop_augment(const lv_patch_item*, int, float*, float*, int, int, cudaStream_t);
 int dp_adamw_pack_step(float*, float*, float*, long long, float, float, float, float, float, int, float, const lv_fused_conv*, int,
                        const void* const*, void* const*, void* const*, const void* const*, double*, uint32_t*, long long, int, int,
                        cudaStream_t);
@@ -260,6 +261,12 @@ int lv_dp_adamw_pack_step(float* param, float* exp_avg, float* exp_avg_sq, int64
   return dp_adamw_pack_step(param, exp_avg, exp_avg_sq, numel, lr, beta1, beta2, eps, weight_decay, step, grad_scale, convs,
                             nconv, peer_grads, peer_reduced, peer_flags, peer_loss, loss_out, ctl, slice, world, rank,
                             static_cast<cudaStream_t>(stream));
+}
+
+int lv_crop_augment(const lv_patch_item* items_dev, int count, float* out_lr, float* out_hr, int patch, int scale,
+                    void* stream) {
+  LV_CHECK_ARG(count == 0 || (items_dev && out_lr && out_hr), "crop_augment: null pointer");
+  return crop_augment(items_dev, count, out_lr, out_hr, patch, scale, static_cast<cudaStream_t>(stream));
 }
 
 int lv_image_to_uint8(const float* src, uint8_t* dst, int64_t numel, void* stream) {

@@ -272,6 +272,65 @@ int psnr_sqsum(const float* out, const float* truth, double* sq_sum, int c, int 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Device-side training-patch pipeline: random crop + rot90 + horizontal flip of an LR / HR image pair that is resident
+// in HBM, written straight into the step's batch tensors (reference dataloaders/div2k_train_loader.py:72-98 on the host,
+// dataloaders/div2k_train_loader_tensor.py:57-97 with torch ops).  One item per patch; out(i, j) of a P x P patch:
+//   undo the flip (j' = P-1-j), undo torch.rot90(k, dims=(1,2)) (k counter-clockwise quarter turns), read the crop.
+struct PatchItem {           // mirrors lv_patch_item
+  const float* lr;           // fp32 [3, h, w]
+  const float* hr;           // fp32 [3, scale*h, scale*w]
+  int h, w, y, x, rot, flip;
+};
+
+__device__ __forceinline__ void unrotate(int i, int j, int P, int rot, int flip, int& si, int& sj) {
+  if (flip) j = P - 1 - j;
+  switch (rot & 3) {
+    case 0: si = i; sj = j; break;
+    case 1: si = j; sj = P - 1 - i; break;            // out = rot90(in, 1): out[i][j] = in[j][P-1-i]
+    case 2: si = P - 1 - i; sj = P - 1 - j; break;
+    default: si = P - 1 - j; sj = i; break;           // rot90(in, 3): out[i][j] = in[P-1-j][i]
+  }
+}
+
+__global__ void __launch_bounds__(256)
+crop_augment_kernel(const PatchItem* __restrict__ items, float* __restrict__ out_lr, float* __restrict__ out_hr, int P, int scale) {
+  const PatchItem it = items[blockIdx.y];
+  const int PH = P * scale;
+  const long long n_lr = 3ll * P * P, n_hr = 3ll * PH * PH;
+  float* dl = out_lr + static_cast<long long>(blockIdx.y) * n_lr;
+  float* dh = out_hr + static_cast<long long>(blockIdx.y) * n_hr;
+  for (long long e = blockIdx.x * 256ll + threadIdx.x; e < n_lr + n_hr; e += static_cast<long long>(gridDim.x) * 256) {
+    const bool hi = e >= n_lr;
+    const long long q = hi ? e - n_lr : e;
+    const int S = hi ? PH : P;
+    const int c = static_cast<int>(q / (static_cast<long long>(S) * S));
+    const int r = static_cast<int>(q - static_cast<long long>(c) * S * S);
+    int si, sj;
+    unrotate(r / S, r % S, S, it.rot, it.flip, si, sj);
+    if (hi) {
+      const int W = it.w * scale, H = it.h * scale;
+      dh[q] = it.hr[(static_cast<long long>(c) * H + it.y * scale + si) * W + it.x * scale + sj];
+    } else {
+      dl[q] = it.lr[(static_cast<long long>(c) * it.h + it.y + si) * it.w + it.x + sj];
+    }
+  }
+}
+
+int crop_augment(const lv_patch_item* items_dev, int count, float* out_lr, float* out_hr, int patch, int scale,
+                 cudaStream_t stream) {
+  if (count == 0) return LV_OK;
+  LV_CHECK_ARG(count > 0 && count <= 65535 && patch > 0 && scale > 0, "crop_augment: bad count / patch / scale");
+  static_assert(sizeof(PatchItem) == sizeof(lv_patch_item), "lv_patch_item layout");
+  const long long per = 3ll * patch * patch * (1 + scale * scale);
+  long long bx = (per + 255) / 256;
+  if (bx > 64) bx = 64;
+  crop_augment_kernel<<<dim3(static_cast<unsigned>(bx), count), 256, 0, stream>>>(
+      reinterpret_cast<const PatchItem*>(items_dev), out_lr, out_hr, patch, scale);
+  LV_LAUNCH_OK();
+  return LV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // AdamW over a flat arena, torch.optim.AdamW semantics (decoupled weight decay, bias-corrected).
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,

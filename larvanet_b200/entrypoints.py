@@ -49,8 +49,11 @@ VALIDATE_FLAGS = [
     ('save_path', str, None, 'Write the upscaled PNGs below this directory.'),
     ('chop_forward', bool, False, 'Upscale in four overlapping quadrants.'),
     ('chop_overlap_size', int, 20, 'Quadrant overlap in LR pixels (even).'),
+    ('exact_bands', int, 0, 'Upscale in K horizontal bands with a receptive-field halo: bounded memory, result identical to '
+                            'the full frame (larvanet_b200/tiling.py; --chop_forward is the reference\'s inexact scheme).'),
 ]
 GET_SR_FLAGS = [
+    ('exact_bands', int, 0, 'Upscale in K horizontal bands with a receptive-field halo (exact; bounds memory on big frames).'),
     ('scale', int, 4, 'Upscaling factor.'),
     ('input_path', str, 'LR', 'Directory of input PNGs.'),
     ('output_path', str, 'SR', 'Directory for the upscaled PNGs.'),
@@ -120,6 +123,17 @@ def _image_psnr(output_image, truth_image):
     return 10.0 * np.log10(255.0 ** 2 / mse)
 
 
+def _upscale_banded_uint8(model, image, bands):
+    """uint8 CHW frame through larvanet_b200.tiling (exact band-sharded inference); None if the plugin has no engine."""
+    net = model.get_model()
+    if not hasattr(net, 'engine'):
+        return None
+    import torch
+    from larvanet_b200 import tiling
+    x = torch.as_tensor(np.asarray([image]), dtype=torch.float32, device=model.device)
+    return tiling.upscale_banded(net.engine(), x, bands, exit_leg=getattr(net, 'leg', None), uint8=True)[0].cpu().numpy()
+
+
 def _save_image(image, path):
     import cv2 as cv
     cv.imwrite(path, cv.cvtColor(np.transpose(image, [1, 2, 0]), cv.COLOR_RGB2BGR))
@@ -146,7 +160,10 @@ def validate_main(argv=None):
             for image_index in range(count):
                 input_image, truth_image, image_name = dataloader.get_image_pair(image_index=image_index, scale=scale)
                 start = time.perf_counter()
-                if args.chop_forward:
+                banded = _upscale_banded_uint8(model, input_image, args.exact_bands) if args.exact_bands > 0 else None
+                if banded is not None:
+                    output_image = banded
+                elif args.chop_forward:
                     output_image = image_utils.upscale_with_chop_forward(model=model, input_image=input_image, scale=scale,
                                                                          overlap_size=args.chop_overlap_size)
                 elif hasattr(model, 'upscale_uint8'):   # round/clip on the device (== _image_to_uint8 below)
@@ -185,7 +202,10 @@ def get_sr_main(argv=None):
         for i, name in enumerate(names):
             image = np.transpose(cv.cvtColor(cv.imread(os.path.join(args.input_path, name)), cv.COLOR_BGR2RGB), [2, 0, 1])
             start = time.perf_counter()
-            if hasattr(model, 'upscale_uint8'):   # round/clip on the device, 4x smaller device->host copy
+            banded = _upscale_banded_uint8(model, image, args.exact_bands) if args.exact_bands > 0 else None
+            if banded is not None:
+                output = banded
+            elif hasattr(model, 'upscale_uint8'):   # round/clip on the device, 4x smaller device->host copy
                 output = model.upscale_uint8(input_list=[image], scale=args.scale)[0]
             else:
                 output = _image_to_uint8(model.upscale(input_list=[image], scale=args.scale)[0])
@@ -309,10 +329,16 @@ def train_main(argv=None, epoch_bookkeeping=False):
             else:
                 input_list, truth_list = dataloader.get_patch_batch(batch_size=local_batch, scale=sc,
                                                                     input_patch_size=args.input_patch_size)
-            yield (torch.from_numpy(np.asarray(input_list, dtype=np.float32)).pin_memory(),
-                   torch.from_numpy(np.asarray(truth_list, dtype=np.float32)).pin_memory())
+            if torch.is_tensor(input_list):      # tensor loaders (reference div2k_train_loader_tensor.py) hand out tensors
+                yield input_list, truth_list
+            else:
+                yield (torch.from_numpy(np.asarray(input_list, dtype=np.float32)).pin_memory(),
+                       torch.from_numpy(np.asarray(truth_list, dtype=np.float32)).pin_memory())
 
-    feeder = DevicePrefetcher(host_batches(), model.device, depth=2)
+    if getattr(dataloader, 'device', None) is not None and getattr(dataloader, 'device').type == 'cuda':
+        feeder = host_batches()   # GPU-resident loader (device-side crop / rot90 / flip): batches are born on the device
+    else:
+        feeder = DevicePrefetcher(host_batches(), model.device, depth=2)
     try:
         while model.global_step < args.max_steps:
             scale = model.get_next_train_scale()

@@ -309,6 +309,12 @@ def psnr_sqsum(out_chw, truth_chw, sq_sum):
                                     _ptr(sq_sum, torch.float64, 'sq_sum'), c, h, w, th, tw, _stream()), 'lv_psnr_sqsum')
 
 
+def crop_augment(items_dev, count, out_lr, out_hr, patch, scale):
+    """Device-side crop + rot90 + flip: `items_dev` = uint8 CUDA tensor holding `count` lv_patch_item records."""
+    check(_lib.load().lv_crop_augment(items_dev.data_ptr(), int(count), _ptr(out_lr, torch.float32, 'out_lr'),
+                                      _ptr(out_hr, torch.float32, 'out_hr'), int(patch), int(scale), _stream()), 'lv_crop_augment')
+
+
 def l1_loss_grad(out_hr, truth_hr, loss_sum, grad_sign=None):
     n, c, h4, w4 = (int(v) for v in out_hr.shape)
     dt = dtype_id(grad_sign.dtype) if grad_sign is not None else LV_F32

@@ -31,6 +31,11 @@ def test_train_validate_get_sr_runtime(tmp_path, script, model):
     assert 'begin training' in out and 'finished' in out and 'psnr=' in out
     losses = [float(l.split('loss ')[1].split(' ')[0]) for l in out.splitlines() if l.startswith('step ') and 'loss ' in l]
     assert losses and all(np.isfinite(losses))
+    # the GPU-resident loader (device-side crop / rot90 / flip) feeds the same loop
+    out2 = _run([script, '--dataloader=synthetic_loader_tensor', '--batch_size=4', '--input_patch_size=24', '--max_steps=4',
+                 '--log_freq=2', '--sleep_ratio=0', '--train_path=' + str(tmp_path / 'train_t'), '--val_volume=1e12',
+                 '--synthetic_images=2', '--synthetic_height=32', '--synthetic_width=40'] + net)
+    assert 'finished' in out2 and 'loss ' in out2
     ckpts = sorted(glob.glob(os.path.join(train_dir, 'model_step*_vol*G.pth')))
     assert ckpts, out
     out = _run(['validate.py', '--restore_path=' + ckpts[-1], '--save_path=' + str(tmp_path / 'val'),
@@ -39,6 +44,11 @@ def test_train_validate_get_sr_runtime(tmp_path, script, model):
     assert glob.glob(str(tmp_path / 'val' / 'x4' / '*.png'))
     out = _run(['validate.py', '--restore_path=' + ckpts[-1], '--chop_forward', '--chop_overlap_size=20'] + net)
     assert 'x4, psnr=' in out
+    # exact band-sharded inference gives the full-frame PSNR to the last digit
+    full = [l for l in _run(['validate.py', '--restore_path=' + ckpts[-1]] + net).splitlines() if l.startswith('x4, psnr=')]
+    band = [l for l in _run(['validate.py', '--restore_path=' + ckpts[-1], '--exact_bands=3'] + net).splitlines()
+            if l.startswith('x4, psnr=')]
+    assert full and band and full[-1].split(',')[1] == band[-1].split(',')[1], (full, band)
     lr_dir = tmp_path / 'lr'
     lr_dir.mkdir()
     rs = np.random.RandomState(0)

@@ -457,6 +457,33 @@ def test_conv_chain_rejects_bad_layers():
         ops.conv3x3_chain(L, torch.zeros(1, dtype=torch.int32, device='cuda'))
 
 
+def test_device_side_crop_rot90_flip_matches_torch():
+    """lv_crop_augment (dataloaders/synthetic_loader_tensor.py) == crop -> torch.rot90(k, dims=(1,2)) -> flip of the last axis,
+    the reference's augmentation (dataloaders/div2k_train_loader_tensor.py:72-93), for every k and both flips."""
+    import importlib
+    ld = importlib.import_module('dataloaders.synthetic_loader_tensor').create_loader()
+    ld.parse_args(['--synthetic_images=3', '--synthetic_height=40', '--synthetic_width=56'])
+    ld.prepare(scales=[4])
+    p = 12
+    draws = [(i % 3, (5 * i) % 29, (7 * i) % 45, 1 + i % 4, (i // 4) % 2) for i in range(8)]
+    x, t = ld.get_patch_batch(len(draws), 4, p, draws=draws)
+    assert x.shape == (8, 3, p, p) and t.shape == (8, 3, 4 * p, 4 * p) and x.is_cuda
+    for b, (idx, y, xx, rot, flip) in enumerate(draws):
+        lr, hr = ld.dev_lr[4][idx], ld.dev_hr[4][idx]
+        rl = torch.rot90(lr[:, y:y + p, xx:xx + p], k=rot, dims=(1, 2))
+        rh = torch.rot90(hr[:, 4 * y:4 * (y + p), 4 * xx:4 * (xx + p)], k=rot, dims=(1, 2))
+        if flip:
+            rl, rh = torch.flip(rl, (2,)), torch.flip(rh, (2,))
+        assert torch.equal(x[b], rl) and torch.equal(t[b], rh), (b, rot, flip)
+    # random draws stay inside the images and reproduce with the seed
+    a1 = ld.get_patch_batch(5, 4, 16)[0].clone()
+    ld2 = importlib.import_module('dataloaders.synthetic_loader_tensor').create_loader()
+    ld2.parse_args(['--synthetic_images=3', '--synthetic_height=40', '--synthetic_width=56'])
+    ld2.prepare(scales=[4])
+    ld2.get_patch_batch(len(draws), 4, p, draws=draws)
+    assert torch.equal(a1, ld2.get_patch_batch(5, 4, 16)[0])
+
+
 def test_uint8_and_psnr_helpers():
     """lv_image_to_uint8 == validate._image_to_uint8 (round-half-even, clip), lv_psnr_sqsum == _fit_truth + _image_psnr."""
     rs = np.random.RandomState(21)
