@@ -149,9 +149,10 @@ class PeerArena:
         self.flag_ptrs = (C.c_void_p * self.world)(*[b + (n + 16) * 4 for b in bases])
         self.reduced_ptrs = (C.c_void_p * self.world)(*[b + (n + ex.TAIL) * 4 for b in bases])
         self.slice = n // self.world                      # numel is padded to a multiple of 128 * world
-        # two-shot from 4 ranks on (one-shot at 8 ranks reads 7 x 3.3 MB per rank: ~30 us); LARVANET_B200_DP_TWO_SHOT=0/1 forces
+        # two-shot at 8 ranks (one-shot would read 7 x 3.3 MB per rank: ~30 us; measured step 0.582 vs 0.600 ms); at 4 ranks
+        # the extra barrier costs more than the 6.6 MB it saves (0.576 vs 0.568 ms).  LARVANET_B200_DP_TWO_SHOT=0/1 forces.
         mode = os.environ.get('LARVANET_B200_DP_TWO_SHOT', 'auto')
-        self.two_shot = (self.world >= 4) if mode == 'auto' else mode == '1'
+        self.two_shot = (self.world >= 8) if mode == 'auto' else mode == '1'
         self.loss_out = torch.zeros(1, dtype=torch.float64, device=ex.storage.device)   # sum over ranks, written by the kernel
         self.ctl = torch.zeros(8, dtype=torch.int32, device=ex.storage.device)
         self.supported = self.world in (2, 4, 8)
