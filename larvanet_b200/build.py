@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(CSRC, 'build')
 LIB = os.path.join(HERE, 'liblarvanet_b200.so')
-SOURCES = ['capi.cu', 'conv_tc.cu', 'conv_row.cu', 'conv_chain.cu', 'conv_simt.cu', 'wgrad.cu', 'head.cu', 'layout.cu']
+SOURCES = ['capi.cu', 'conv_tc.cu', 'conv_row.cu', 'conv_row_cp.cu', 'conv_chain.cu', 'conv_simt.cu', 'wgrad.cu', 'head.cu', 'layout.cu']
 # measured-slower experiments of round 1 (cluster-resident strips, ky-stacked tiles with a shuffle epilogue) live in
 # tools/experiments/ and are only compiled into the library with LARVANET_B200_EXPERIMENTAL=1 (adds -DLV_EXPERIMENTAL)
 EXPERIMENTAL = os.environ.get('LARVANET_B200_EXPERIMENTAL', '0') == '1'
