@@ -35,6 +35,22 @@
 #include "conv_epilogue.cuh"
 #include "lv_common.cuh"
 
+// 48-channel build: 8 row buffers + 2 weight buffers (190 KB).  The third weight buffer of the first version bought
+// nothing; eight instead of five row buffers cut the rows the scheduler finds "not staged yet" from 37 % to 21 %.
+#ifndef LV_ROW_STAGES48
+#define LV_ROW_STAGES48 8
+#define LV_ROW_WBUFS48 2
+#endif
+#ifndef LV_ROW_DBG_NOSPLIT
+#define LV_ROW_DBG_NOSPLIT 0
+#endif
+#ifndef LV_ROW_DBG_NOEPI
+#define LV_ROW_DBG_NOEPI 0
+#endif
+#ifndef LV_ROW_DBG_NOPROD
+#define LV_ROW_DBG_NOPROD 0
+#endif
+
 namespace lv {
 
 extern int g_use_pdl;
@@ -44,29 +60,42 @@ namespace LV_ROW_NS {
 
 constexpr int kMaxLayers = 96;   // LV_CHAIN_MAX_LAYERS
 constexpr int kLanes = 128, kRowPx = kLanes + 2;
-// Warp roles (416 threads): 0-7 epilogue (two groups), 8 MMA issuer, 9 scheduler, 10-11 row producers, 12 publisher.
+// Warp roles: 0-7 epilogue (two groups of 4 warps), 8 MMA issuer, 9 scheduler, 10(-11) row producer(s), last: publisher.
 // Why a scheduler warp: the tensor pipe's instruction queue holds only ~4 MMAs (~270 clk of work), and ONE thread that
 // waits for the accumulator block and the input row, computes the row's descriptors, issues and commits spends ~1,100 clk
 // per row outside the issue loop (measured: 2,330 clk per row for 680 clk of MMAs, tensor pipe 29 % busy; the 16x8-tile
 // kernels pay the same ~1,000 clk per tile).  So everything but the issue itself moves to a second thread: the scheduler
 // waits, computes, and hands the issuer a ready-made command (descriptors, accumulate flags, barriers to commit to)
-// through a 4-deep shared-memory ring; the issuer's gap between two rows is one mbarrier wait + two 16-byte loads.
+// through a 16-deep shared-memory ring guarded by two counters (`published`, `consumed`): the issuer takes every row
+// that is ready with ONE poll and fetches the next command while the current row's MMAs sit in the tensor queue.
 // Row loads: 1-D TMA bulk copies (one per 8-channel chunk and per run of consecutive pixels of one image, pad pixels
 // from a zero page) issued by ONE producer warp -- against 26 warp-wide cp.async instructions per row on two warps they
 // take the row fill off the LSU path (which the MMAs' operand reads starve, see below) and give a warp back: 12 warps
-// = 168 registers per thread instead of 13 warps = 128.  -DLV_ROW_CPASYNC builds the cp.async producers for A/B runs.
+// = 168 registers per thread instead of 13 warps = 128.  -DLV_ROW_CPASYNC builds the cp.async producers (conv_row_cp.cu).
+// Two measured properties of the tensor pipe shape the issue order (tools/probes/row_probe.cu, tools/row_trace.py):
+//   * consecutive MMAs into the SAME accumulator address pipeline at the nominal rate (N=144: 73 clk), and moving to a
+//     new address once per row is free, but ALTERNATING between two addresses costs ~110 clk per switch -- rows whose
+//     three targets straddle the ring's wrap issue their two runs one after the other, never interleaved (interleaved
+//     they cost +2,000 clk per such row, i.e. 40 % of the kernel's time);
+//   * an N=144 MMA reads 8.6 KB of operands in 73 clk = 92 % of the shared-memory port, so while MMAs execute every other
+//     warp's shared-memory / LSU instruction waits 100-300 clk: all other roles are written to need few of them.
 #ifdef LV_ROW_CPASYNC
 constexpr bool kTmaRows = false;
 #else
 constexpr bool kTmaRows = true;
 #endif
-constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = kTmaRows ? 32 : 64;
+#ifndef LV_ROW_EPI_GROUPS
+#define LV_ROW_EPI_GROUPS 2
+#endif
+constexpr int kEpiGroups = LV_ROW_EPI_GROUPS;             // groups of 4 warps (one per TMEM lane quarter); output row kk
+                                                          // is drained by group kk % kEpiGroups
+constexpr int kEpiWarps = 4 * kEpiGroups, kEpiThreads = kEpiWarps * 32, kProdThreads = kTmaRows ? 32 : 64;
 constexpr int kMmaWarp = kEpiWarps;                       // 8
 constexpr int kSchedWarp = kMmaWarp + 1;                  // 9
 constexpr int kProdWarp0 = kSchedWarp + 1;                // 10 (, 11)
 constexpr int kPubWarp = kProdWarp0 + kProdThreads / 32;  // 11 (12)
 constexpr int kThreads = (kPubWarp + 1) * 32;             // 384 (416)
-constexpr int kCmdSlots = 4;
+constexpr int kCmdSlots = 16;
 
 __device__ uint4 g_zero_page[kLanes + 2];                 // source of the pad / out-of-range pixels' bulk copies (zeros)
 
@@ -103,6 +132,18 @@ __device__ __forceinline__ void stat_add(const Geom& g, int slot, long long v) {
   if (g.stats != nullptr && blockIdx.x == 0) g.stats[slot] += v;
 }
 __device__ __forceinline__ long long stat_clk(const Geom& g) { return g.stats != nullptr ? clock64() : 0; }
+// Developer trace (-DLV_ROW_TRACE=1, tools/row_trace.py): absolute clock64() stamps of CTA 0's roles for rows
+// [kTraceFirst, kTraceFirst + kTraceRows) of the CTA's row counters, behind the 64 counters of the stats buffer.
+#ifndef LV_ROW_TRACE
+#define LV_ROW_TRACE 0
+#endif
+constexpr uint32_t kTraceFirst = 100, kTraceRows = 64;
+__device__ __forceinline__ void trace(const Geom& g, int role, uint32_t idx, int ev) {
+#if LV_ROW_TRACE
+  if (g.stats != nullptr && blockIdx.x == 0 && idx - kTraceFirst < kTraceRows)
+    g.stats[64 + (role * kTraceRows + (idx - kTraceFirst)) * 4 + ev] = clock64();
+#endif
+}
 
 // Shared-memory budget: stay below the 196 KB carve-out step so that the SM keeps ~32 KB of L1 (kernel parameters,
 // bias vectors, whatever the epilogue spills): with the 228 KB step nothing is left and every such access goes to L2.
@@ -121,7 +162,7 @@ struct Cfg {
   static constexpr int PIECES = (kRowPx * CH + kProdThreads - 1) / kProdThreads;
   static constexpr int ONES_TILE = 2 * kLanes * 16;  // A operand of the bias MMA: [2 K-halves][128 rows][16 B], (1,1,0,..) / 0
   static constexpr int BIAS_TILE = 2 * NT * 16;      // B operand: [2 K-halves][cout rows][16 B], row n = (hi(b_n), lo(b_n), 0,..)
-  static constexpr int NBARS = 2 * NSTAGE + 2 * RING + 3 * WBUFS + 4 + 2 * kCmdSlots;
+  static constexpr int NBARS = 2 * NSTAGE + 2 * RING + 3 * WBUFS + 4;
   static constexpr size_t smem_bytes() {
     return static_cast<size_t>(WBUFS) * (W_LAYER + BIAS_TILE) + ONES_TILE + static_cast<size_t>(NSTAGE) * A_STAGE +
            kCmdSlots * sizeof(RowCmd) + NBARS * 8 + 64;
@@ -152,6 +193,14 @@ __device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t need) {
   (void)ld_acquire_gpu(p);
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& t) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w) : "memory");
 }
@@ -303,19 +352,21 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
     }
     for (int yo = y0; yo < y1; ++yo) {
       const uint32_t kk = k + static_cast<uint32_t>(yo - y0);
-      if ((kk & 1u) != static_cast<uint32_t>(cx.eg)) continue;
+      if (kk % static_cast<uint32_t>(kEpiGroups) != static_cast<uint32_t>(cx.eg)) continue;
       const uint32_t blk = kk % RING;
       const uint32_t par = (kk / RING) & 1u;
       const uint32_t taddr = cx.tmem_lane + (RING - 1 - blk) * NT;
       const uint32_t tfull = cx.tfull0 + 8u * blk, tempty = cx.tempty0 + 8u * blk;
       const size_t o0 = o_img + static_cast<size_t>(yo) * cx.row_stride;
       const uint32_t seen = (cx.nlayers > 1) ? *cx.pub_seen : 0u;
-      const bool st = cx.g.stats != nullptr && cx.lane == 0 && (cx.m == 0);
+      const bool st = cx.g.stats != nullptr && cx.lane == 0 && (cx.m == 0) && cx.eg < 2;
       long long c0 = 0, c1 = 0;
       if (cx.g.stats != nullptr) {       // debug only: separate "waiting for the accumulator" from "draining it"
         c0 = clock64();
+        if (st) trace(cx.g, 3 + cx.eg, kk, 0);
         mbar_wait_relaxed(tfull, par);
         c1 = clock64();
+        if (st) trace(cx.g, 3 + cx.eg, kk, 1);
       }
       if constexpr (KIND == kKindPs4) {
         loss += chain::ps4_tile<NT>(a, nullptr, valid, n, yo, x, cx.g.H, cx.g.W, o0, cx.chunk_stride, taddr, tfull, tempty, par);
@@ -332,9 +383,17 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
         tc_fence_before_sync();
         mbar_arrive(tempty);
       } else {
+#if LV_ROW_DBG_NOEPI   // timing experiment: no TMEM drain, no global traffic (results are garbage)
+        mbar_wait_relaxed(tfull, par);
+        tc_fence_after_sync();
+        tc_fence_before_sync();
+        mbar_arrive(tempty);
+#else
         row_tile<KIND, NT>(fe, valid, o0, cx.chunk_stride, taddr, tfull, tempty, par, st ? dbgv : nullptr);
+#endif
       }
       if (st) {
+        trace(cx.g, 3 + cx.eg, kk, 2);
         st_wait += c1 - c0;
         st_drain += clock64() - c1;
         st_rows += 1;
@@ -359,7 +418,7 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
     loss = warp_sum(loss);
     if (cx.lane == 0) atomicAdd(a.loss_sum, static_cast<double>(loss));
   }
-  if (cx.g.stats != nullptr && cx.lane == 0 && cx.m == 0) {
+  if (cx.g.stats != nullptr && cx.lane == 0 && cx.m == 0 && cx.eg < 2) {
     const int base = 16 + 8 * cx.eg;
     stat_add(cx.g, base + 0, st_wait);
     stat_add(cx.g, base + 1, st_drain);
@@ -399,11 +458,11 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
   auto empty_idx = [&](int s) { return static_cast<uint32_t>(NSTAGE + s); };
   auto tfull_idx = [&](uint32_t b) { return static_cast<uint32_t>(2 * NSTAGE) + b; };
   auto wfree_idx = [&](int b) { return static_cast<uint32_t>(2 * NSTAGE + 2 * RING + WBUFS + b); };
-  auto cmd_full_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 3 * WBUFS + 4 + s); };
-  auto cmd_free_bar = [&](int s) { return bar0 + 8u * (2 * NSTAGE + 2 * RING + 3 * WBUFS + 4 + kCmdSlots + s); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C_::NBARS);
   uint32_t* s_last = tmem_slot + 1;
   volatile uint32_t* pub_seen = tmem_slot + 2;   // rows whose completion the publisher warp has observed
+  volatile uint32_t* cmd_published = tmem_slot + 4;   // command ring: rows written by the scheduler ...
+  volatile uint32_t* cmd_consumed = tmem_slot + 8;    // ... and rows the issuer has taken
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -412,19 +471,17 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
     }
     for (int b = 0; b < RING; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), kEpiThreads / 2);
+      mbar_init(tempty_bar(b), kEpiThreads / kEpiGroups);
     }
     for (int b = 0; b < WBUFS; ++b) {
       mbar_init(wfull_bar(b), 1);
       mbar_init(wfree_bar(b), 1);
       mbar_init(bfull_bar(b), kProdThreads);
     }
-    for (int s = 0; s < 4; ++s) mbar_init(pub_bar(s), kEpiWarps / 2);
-    for (int s = 0; s < kCmdSlots; ++s) {
-      mbar_init(cmd_full_bar(s), 1);
-      mbar_init(cmd_free_bar(s), 1);
-    }
+    for (int s = 0; s < 4; ++s) mbar_init(pub_bar(s), kEpiWarps / kEpiGroups);
     tmem_slot[2] = 0u;
+    tmem_slot[4] = 0u;
+    tmem_slot[8] = 0u;
     mbar_fence_init();
   }
   // constant A operand of the bias MMA: K columns 0 and 1 are ones (they meet the bias' hi and lo parts), the rest zero;
@@ -560,17 +617,23 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
             const long long pc1 = stat_clk(g);
             if (lane == 0) {
               mbar_wait_relaxed(empty_bar(stage), ((fill / NSTAGE) & 1) ^ 1);
+#if LV_ROW_DBG_NOPROD   // timing experiment: rows are never copied (results are garbage)
+              mbar_arrive(full_bar(stage));
+#else
               mbar_arrive_expect_tx(full_bar(stage), C_::A_STAGE);
+#endif
             }
             __syncwarp();
             const long long pc2 = stat_clk(g);
-            if (mine) {
+            if (lane == 0) trace(g, 0, fill, 0);
+            if (mine && !LV_ROW_DBG_NOPROD) {
               const __nv_bfloat16* src = src_base + static_cast<size_t>(yi) * row_stride;
               tma_bulk_g2s(smem_u32(sA + stage * C_::A_STAGE) + m_dst,
                            m_off >= 0 ? static_cast<const void*>(src + m_off) : static_cast<const void*>(g_zero_page), m_bytes,
                            full_bar(stage));
             }
             sp_empty += pc2 - pc1;                 // waiting for a free row buffer
+            if (lane == 0) trace(g, 0, fill, 1);
             sp_issue += stat_clk(g) - pc2;         // issuing the copies
             sp_rows += 1;
           }
@@ -617,6 +680,11 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
     }
   } else if (warp == kSchedWarp) {
     // =============================== scheduler: waits + descriptors -> command ring ================================
+    // One thread.  Under MMA load every shared-memory round trip of another warp (an mbarrier probe, a load) costs
+    // 150-300 clk, so the loop is arranged to pay ONE per row: the row's barrier probes are issued first and their
+    // results looked at only after the descriptor arithmetic; commands are handed over through a pair of counters
+    // (`published` here, `consumed` in the issuer) instead of a barrier per slot, so that the issuer can take every row
+    // that is ready with one poll.
     if (lane == 0) {
       auto load_weights = [&](int l) {
         const int b = l % WBUFS;
@@ -627,8 +695,12 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
                        C_::W_PLANE, wfull_bar(b));
       };
       load_weights(0);   // packed weights are never written while a launch chain is in flight: no pdl_wait needed
-      uint32_t fill = 0, k = 0, ncmd = 0;
-      long long ss_setup = 0, ss_tempty = 0, ss_full = 0, ss_slot = 0, ss_rows = 0;   // debug counters (registers)
+      uint32_t k = 0, ncmd = 0, cons = 0, fph = 0;   // fph: parity of the row buffer's current use
+      int stage = 0;
+      const uint32_t a_lo0 = static_cast<uint32_t>(umma_smem_desc(smem_u32(sA), C_::A_PLANE, 128));
+      const uint32_t cmd0 = smem_u32(cmds);
+      const uint32_t pub_addr = smem_u32(const_cast<uint32_t*>(cmd_published)), cons_addr = smem_u32(const_cast<uint32_t*>(cmd_consumed));
+      long long ss_setup = 0, ss_wait = 0, ss_slot = 0, ss_write = 0, ss_rows = 0, ss_nf = 0, ss_nt = 0;   // debug counters
       for (int l = 0; l < nlayers; ++l) {
         const int wb = l % WBUFS;
         if (l + 1 < nlayers) {
@@ -648,99 +720,146 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
         for (int job = first_job(l); job < g.total_jobs; job += G) {
           const Job j = decode(job);
           const int ya = max(j.y0 - 1, 0), yb = min(j.y1 + 1, g.H);
-          for (int yi = ya; yi < yb; ++yi, ++fill, ++ncmd) {
+          // Accumulator-ring position of "target 0" (output row yi + 1) of the job's first input row: counter kk0, block
+          // m0 = kk0 % RING at column (RING-1 - m0) * NT, use parity ph0 = (kk0 / RING) & 1; all of it advances by one per
+          // row, so the loop below carries it along instead of dividing (this thread's ALU time is on the critical path:
+          // 400 clk of setup per row held the whole CTA at ~1,100 clk per row)
+          const uint32_t kk_first = k + static_cast<uint32_t>(ya + 1 - j.y0);
+          uint32_t m0 = kk_first % RING, ph0 = (kk_first / RING) & 1u;
+          for (int yi = ya; yi < yb; ++yi, ++ncmd) {
             const long long c0 = stat_clk(g);
-            // targets t = 0,1,2: output row yi+1-t through vertical tap ky = t (weight rows [t*NT, (t+1)*NT));
-            // the valid ones form an interval [ta, tb]
-            int ta = 3, tb = -1;
-#pragma unroll
-            for (int t = 0; t < 3; ++t) {
-              const int r = yi + 1 - t;
-              if (r >= j.y0 && r < j.y1) { ta = min(ta, t); tb = t; }
-            }
-            // accumulator-ring counter of target t's output row; its block sits at column (RING-1 - kk % RING) * NT,
-            // so the blocks of targets t, t+1 are adjacent (ascending) unless kk_t % RING == 0 (the ring wraps there)
-            const uint32_t kk0 = k + static_cast<uint32_t>(yi + 1 - j.y0);      // target 0 (may be "virtual" when invalid)
-            auto col_of = [&](int t) { return (RING - 1 - ((kk0 - static_cast<uint32_t>(t)) % RING)) * NT; };
-            // Runs = maximal groups of valid targets issued as ONE MMA (adjacent blocks, N = NT * targets): A = [ta..ea],
-            // B = [ea+1..tb] (only when the ring wraps inside the interval).  Blocks that get their FIRST contribution
-            // from this input row (target 0 always; target 1 too on the image's top row) are initialised by the bias MMA.
-            int ea = ta;
-            while (ea < tb && ((kk0 - static_cast<uint32_t>(ea)) % RING) != 0) ++ea;
-            const bool has_b = ea < tb;
+            trace(g, 1, ncmd, 0);
+            // the row is staged; blocks that get their FIRST contribution from this input row (target 0 always; target 1
+            // too on the image's top row) have been drained by the epilogue (their previous output row): probe the three
+            // barriers now, look at the answers after the arithmetic below
+            const uint32_t m1 = m0 ? m0 - 1u : RING - 1u, ph1 = m0 ? ph0 : ph0 ^ 1u;
+            const uint32_t m2 = m1 ? m1 - 1u : RING - 1u;
+            // targets t = 0,1,2: output row yi+1-t through vertical tap ky = t (weight rows [t*NT, (t+1)*NT)); the valid
+            // ones (row inside the job) form the interval [ta, tb]
+            const int ta = max(0, yi + 2 - j.y1), tb = min(2, yi + 1 - j.y0);
             const bool fresh0 = ta == 0, fresh1 = yi == 0 && ta <= 1 && tb >= 1;
-            const int stage = fill % NSTAGE;
-            const uint32_t tfa = (yi - 1 >= j.y0 && yi - 1 < j.y1) ? 1u + tfull_idx((k + static_cast<uint32_t>(yi - 1 - j.y0)) % RING) : 0u;
-            const uint32_t tfb = (yi == g.H - 1 && yi >= j.y0 && yi < j.y1) ? 1u + tfull_idx((k + static_cast<uint32_t>(yi - j.y0)) % RING) : 0u;
+            const uint32_t bar_t0 = tempty_bar(m0), bar_t1 = tempty_bar(m1), bar_f = full_bar(stage);
+            bool ok_t0 = !fresh0 || mbar_try_wait(bar_t0, ph0 ^ 1u);
+            bool ok_t1 = !fresh1 || mbar_try_wait(bar_t1, ph1 ^ 1u);
+            bool ok_f = mbar_try_wait(bar_f, fph);
+            // Runs = maximal groups of valid targets issued as ONE MMA (blocks of targets t, t+1 are adjacent, ascending,
+            // unless target t sits in block 0 = the ring wraps there; N = NT * targets): A = [ta..ea], B = [ea+1..tb]
+            // (only when the ring wraps inside the interval); fresh blocks are initialised by the bias MMA
+            const uint32_t m_ta = ta == 0 ? m0 : ta == 1 ? m1 : m2;
+            int ea = ta;
+            if (ea < tb && (ea == 0 ? m0 : m1) != 0u) ++ea;
+            if (ea < tb && (ea == 0 ? m0 : m1) != 0u) ++ea;
+            const bool has_b = ea < tb;
+            const uint32_t m_eb = ea == 0 ? m1 : m2;                      // first block of run B
+            const uint32_t tfa = tb == 2 ? 1u + tfull_idx(m2) : 0u;       // output row yi-1 gets its last contribution
+            const uint32_t tfb = (yi == g.H - 1 && ta <= 1 && tb >= 1) ? 1u + tfull_idx(m1) : 0u;   // bottom row: row yi too
             const uint32_t wfr = (job == last_job && yi == yb - 1) ? 1u + wfree_idx(wb) : 0u;
-            const uint4 q0 = make_uint4(static_cast<uint32_t>(umma_smem_desc(smem_u32(sA + stage * C_::A_STAGE), C_::A_PLANE, 128)),
-                                        b_lo, tmem_base + col_of(ta), static_cast<uint32_t>(ta * NT));
-            const uint4 q1 = make_uint4(idesc_n((ea - ta + 1) * NT), tmem_base + col_of(ea + 1), static_cast<uint32_t>((ea + 1) * NT),
-                                        has_b ? idesc_n((tb - ea) * NT) : 0u);
-            const uint4 q2 = make_uint4(fresh0 ? tmem_base + col_of(0) : kNoBlock, fresh1 ? tmem_base + col_of(1) : kNoBlock,
+            const uint4 q0 = make_uint4(a_lo0 + static_cast<uint32_t>(stage) * (C_::A_STAGE >> 4), b_lo,
+                                        tmem_base + (RING - 1u - m_ta) * NT, static_cast<uint32_t>(ta * NT));
+            const uint4 q1 = make_uint4(idesc_n((ea - ta + 1) * NT), tmem_base + (RING - 1u - m_eb) * NT,
+                                        static_cast<uint32_t>((ea + 1) * NT), has_b ? idesc_n((tb - ea) * NT) : 0u);
+            const uint4 q2 = make_uint4(fresh0 ? tmem_base + (RING - 1u - m0) * NT : kNoBlock,
+                                        fresh1 ? tmem_base + (RING - 1u - m1) * NT : kNoBlock,
                                         empty_idx(stage) | (tfa << 8) | (tfb << 16) | (wfr << 24), bias_lo);
             const long long c1 = stat_clk(g);
-            // blocks initialised by this row must have been drained by the epilogue (their previous output row)
-            if (fresh0) mbar_wait(tempty_bar(kk0 % RING), ((kk0 / RING) & 1u) ^ 1u);
-            if (fresh1) {
-              const uint32_t kk1 = kk0 - 1u;
-              mbar_wait(tempty_bar(kk1 % RING), ((kk1 / RING) & 1u) ^ 1u);
+            if (g.stats != nullptr) { ss_nf += ok_f ? 0 : 1; ss_nt += (ok_t0 && ok_t1) ? 0 : 1; }
+            {
+              uint32_t spins = 0;
+              while (!(ok_t0 && ok_t1 && ok_f)) {
+                if (!ok_t0) ok_t0 = mbar_try_wait(bar_t0, ph0 ^ 1u);
+                if (!ok_t1) ok_t1 = mbar_try_wait(bar_t1, ph1 ^ 1u);
+                if (!ok_f) ok_f = mbar_try_wait(bar_f, fph);
+                if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+              }
             }
+            trace(g, 1, ncmd, 1);
             const long long c2 = stat_clk(g);
-            mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
-            const long long c3 = stat_clk(g);
-            const uint32_t slot = ncmd % kCmdSlots;
-            mbar_wait(cmd_free_bar(slot), ((ncmd / kCmdSlots) & 1u) ^ 1u);
-            uint4* dst = reinterpret_cast<uint4*>(&cmds[slot]);
-            st_shared_v4(smem_u32(dst), q0);
-            st_shared_v4(smem_u32(dst + 1), q1);
-            st_shared_v4(smem_u32(dst + 2), q2);
-            mbar_arrive(cmd_full_bar(slot));   // release: the command (and the barrier completions observed above)
-            if (g.stats != nullptr) {
-              ss_setup += c1 - c0; ss_tempty += c2 - c1; ss_full += c3 - c2; ss_slot += clock64() - c3; ss_rows += 1;
+            // a free slot of the command ring: the issuer's counter is re-read only when the cached value says "full"
+            if (ncmd - cons >= static_cast<uint32_t>(kCmdSlots)) {
+              uint32_t spins = 0;
+              while (ncmd - (cons = ld_acquire_shared(cons_addr)) >= static_cast<uint32_t>(kCmdSlots))
+                if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
             }
+            trace(g, 1, ncmd, 2);
+            const long long c3 = stat_clk(g);
+            const uint32_t dst = cmd0 + (ncmd % kCmdSlots) * static_cast<uint32_t>(sizeof(RowCmd));
+            st_shared_v4(dst, q0);
+            st_shared_v4(dst + 16, q1);
+            st_shared_v4(dst + 32, q2);
+            st_release_shared(pub_addr, ncmd + 1u);   // release: the command and the barrier completions observed above
+            trace(g, 1, ncmd, 3);
+            if (g.stats != nullptr) {
+              ss_setup += c1 - c0; ss_wait += c2 - c1; ss_slot += c3 - c2; ss_write += clock64() - c3; ss_rows += 1;
+            }
+            if (++m0 == RING) { m0 = 0u; ph0 ^= 1u; }
+            if (++stage == NSTAGE) { stage = 0; fph ^= 1u; }
           }
           k += static_cast<uint32_t>(j.y1 - j.y0);
         }
       }
       // terminating command
       {
-        const uint32_t slot = ncmd % kCmdSlots;
-        mbar_wait(cmd_free_bar(slot), ((ncmd / kCmdSlots) & 1u) ^ 1u);
-        st_shared_v4(smem_u32(&cmds[slot]), make_uint4(kCmdStop, 0u, 0u, 0u));
-        mbar_arrive(cmd_full_bar(slot));
+        uint32_t spins = 0;
+        while (ncmd - cons >= static_cast<uint32_t>(kCmdSlots)) {
+          cons = ld_acquire_shared(cons_addr);
+          if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+        }
+        st_shared_v4(smem_u32(&cmds[ncmd % kCmdSlots]), make_uint4(kCmdStop, 0u, 0u, 0u));
+        st_release_shared(pub_addr, ncmd + 1u);
       }
-      stat_add(g, 0, ss_setup); stat_add(g, 4, ss_tempty); stat_add(g, 1, ss_full); stat_add(g, 5, ss_slot);
-      stat_add(g, 3, ss_rows);
+      stat_add(g, 0, ss_setup); stat_add(g, 4, ss_wait); stat_add(g, 1, ss_slot); stat_add(g, 5, ss_write);
+      stat_add(g, 3, ss_rows); stat_add(g, 13, ss_nf); stat_add(g, 14, ss_nt);
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer (one elected lane): executes the command ring =======================
     if (elect_one()) {
-      long long si_wait = 0, si_issue = 0, si_commit = 0;   // debug counters (registers)
+      long long si_wait = 0, si_issue = 0, si_commit = 0, si_polls = 0;   // debug counters (registers)
       // high word of both operand descriptors: SBO = 128 B (8 rows x 16 B core matrices), descriptor version 1; the low
       // word (start address + LBO) comes with the command
       constexpr uint64_t kDescHi = (static_cast<uint64_t>((128 >> 4) & 0x3fff) << 32) | (static_cast<uint64_t>(1) << 46);
       const uint64_t ones_desc = umma_smem_desc(smem_u32(sOnes), kLanes * 16, 128);
+      const uint32_t pub_addr = smem_u32(const_cast<uint32_t*>(cmd_published)), cons_addr = smem_u32(const_cast<uint32_t*>(cmd_consumed));
+      // `pub` rows are known to be published; row n's command is in w0..w2.  The next command is fetched BEFORE this
+      // row's MMAs are issued whenever it is already known to be there, so that its loads land while the issue loop is
+      // blocked on the tensor queue; `published` is polled again only when the known rows run out.
+      uint32_t pub = 0;
+      uint4 w0, w1, w2;
+      bool have = false;
       for (uint32_t n = 0;; ++n) {
-        const uint32_t slot = n % kCmdSlots;
         const long long c0 = stat_clk(g);
-        mbar_wait(cmd_full_bar(slot), (n / kCmdSlots) & 1u);
-        const uint32_t ca = smem_u32(&cmds[slot]);
-        const uint4 w0 = ld_shared_v4(ca);
+        if (!have) {
+          uint32_t spins = 0;
+          while (pub <= n) {
+            pub = ld_acquire_shared(pub_addr);
+            si_polls += 1;
+            if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
+          }
+          const uint32_t ca = smem_u32(&cmds[n % kCmdSlots]);
+          w0 = ld_shared_v4(ca); w1 = ld_shared_v4(ca + 16); w2 = ld_shared_v4(ca + 32);
+        }
         if (w0.x == kCmdStop) break;
-        const uint4 w1 = ld_shared_v4(ca + 16), w2 = ld_shared_v4(ca + 32);
-        mbar_arrive(cmd_free_bar(slot));
-        fence_proxy_async_smem();   // cp.async (generic proxy) writes of the row -> UMMA (async proxy) reads
+        trace(g, 2, n, 0);
+        uint4 n0, n1, n2;
+        have = pub > n + 1u;
+        if (have) {
+          const uint32_t nca = smem_u32(&cmds[(n + 1u) % kCmdSlots]);
+          n0 = ld_shared_v4(nca); n1 = ld_shared_v4(nca + 16); n2 = ld_shared_v4(nca + 32);
+        }
+        if (!kTmaRows) fence_proxy_async_smem();   // cp.async (generic proxy) writes of the row -> UMMA (async proxy) reads;
+                                                    // rows written by bulk copies are already in the async proxy
         tc_fence_after_sync();
         const long long c1 = stat_clk(g);
         // RowCmd fields: w0 = {a_lo, b_lo, ra_d, ra_b}, w1 = {ra_i, rb_d, rb_b, rb_i}, w2 = {f0_d, f1_d, bars, bias_lo}
         const uint64_t adesc0 = kDescHi | w0.x;
         const uint64_t bdesc0 = kDescHi | w0.y;
-        const bool has_b = w1.w != 0u;
+        // LV_ROW_DBG_NOSPLIT (bit 0: no split MMAs at ring wraps, bit 1: no bias MMAs): timing experiments, results garbage
+        const bool has_b = (LV_ROW_DBG_NOSPLIT & 1) ? false : (w1.w != 0u);
         // blocks that get their first contribution from this row: D = ones x bias tile (overwrite)
-        if (w2.x != kNoBlock) umma_bf16(w2.x, ones_desc, kDescHi | w2.w, idesc_n(NT), 0u);
-        if (w2.y != kNoBlock) umma_bf16(w2.y, ones_desc, kDescHi | w2.w, idesc_n(NT), 0u);
+        if (!(LV_ROW_DBG_NOSPLIT & 2)) {
+          if (w2.x != kNoBlock) umma_bf16(w2.x, ones_desc, kDescHi | w2.w, idesc_n(NT), 0u);
+          if (w2.y != kNoBlock) umma_bf16(w2.y, ones_desc, kDescHi | w2.w, idesc_n(NT), 0u);
+        }
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
@@ -749,18 +868,35 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
             const uint64_t adesc = adesc0 + static_cast<uint64_t>((kx * 16 + 2 * ks * C_::A_PLANE) >> 4);
             const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((kx * C_::W_KX + 2 * ks * C_::W_PLANE) >> 4);
             umma_bf16(w0.z, adesc, bdesc + w0.w, w1.x, 1u);
-            if (has_b) umma_bf16(w1.y, adesc, bdesc + w1.z, w1.w, 1u);
+            trace(g, 5 + ((kx * C_::KSTEPS + ks) >> 2), n, (kx * C_::KSTEPS + ks) & 3);
+          }
+        }
+        // the second run of a row whose targets straddle the ring's wrap, AFTER the first one: alternating between two
+        // accumulator addresses costs the tensor pipe ~110 clk per switch (measured: +2,000 clk per such row)
+        if (has_b) {
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+            for (int ks = 0; ks < C_::KSTEPS; ++ks) {
+              const uint64_t adesc = adesc0 + static_cast<uint64_t>((kx * 16 + 2 * ks * C_::A_PLANE) >> 4);
+              const uint64_t bdesc = bdesc0 + static_cast<uint64_t>((kx * C_::W_KX + 2 * ks * C_::W_PLANE) >> 4);
+              umma_bf16(w1.y, adesc, bdesc + w1.z, w1.w, 1u);
+            }
           }
         }
         const long long c2 = stat_clk(g);
+        trace(g, 2, n, 1);
         const uint32_t bi = w2.z;
         umma_commit(bar0 + 8u * (bi & 0xffu));                                         // row buffer reusable once these MMAs retire
         if ((bi >> 8) & 0xffu) umma_commit(bar0 + 8u * (((bi >> 8) & 0xffu) - 1u));    // output row yi-1 complete
         if ((bi >> 16) & 0xffu) umma_commit(bar0 + 8u * (((bi >> 16) & 0xffu) - 1u));  // image's bottom row: row yi complete
         if (bi >> 24) umma_commit(bar0 + 8u * ((bi >> 24) - 1u));                      // layer's last row: weight buffer free
+        st_release_shared(cons_addr, n + 1u);   // the command's words are in registers: its slot may be rewritten
+        trace(g, 2, n, 2);
+        if (have) { w0 = n0; w1 = n1; w2 = n2; }
         if (g.stats != nullptr) { si_wait += c1 - c0; si_issue += c2 - c1; si_commit += clock64() - c2; }
       }
-      stat_add(g, 2, si_issue); stat_add(g, 6, si_commit); stat_add(g, 7, si_wait);
+      stat_add(g, 2, si_issue); stat_add(g, 6, si_commit); stat_add(g, 7, si_wait); stat_add(g, 12, si_polls);
     }
     __syncwarp();
   } else {
@@ -921,7 +1057,7 @@ static int launch_row(const lv_conv_args* layers, int count, void* sync_ws, long
 // by the dispatcher conv3x3_row_chain (conv_row.cu)
 int LV_ROW_ENTRY(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
                  cudaStream_t stream) {
-  if (layers[0].cin == 48) return launch_row<48, 48, 5, 3>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
+  if (layers[0].cin == 48) return launch_row<48, 48, LV_ROW_STAGES48, LV_ROW_WBUFS48>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
   return launch_row<64, 64, 2, 2>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
 }
 

@@ -1,6 +1,7 @@
 // Micro-benchmark of the row-marching MMA pattern (conv_row.cu): per input row one N=48 overwrite + one N=96 accumulate +
 // 8 x N=144 accumulate MMAs whose D blocks move through a ring of 10 x 48 TMEM columns, against plain N=144 MMAs on a fixed D.
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "../../larvanet_b200/csrc/lv_common.cuh"
@@ -17,13 +18,14 @@ __device__ __forceinline__ uint32_t idesc_n(int n) {
 // VAR 3: VAR 2 + two tcgen05.commit per row
 // VAR 4: VAR 3 + fence.proxy.async + tcgen05 fence per row
 // VAR 5: 30 x N=48 on D column 0 (tap-major cost for reference)
+__device__ int g_random;
 template <int VAR>
 __global__ void __launch_bounds__(128, 1) probe(int rows, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar[16];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = g_random ? (0x3c003c00u ^ ((i * 2654435761u) >> 9 & 0x03ff83ffu)) : 0x3c003c00u;
   if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&bar[i]), 1); mbar_fence_init(); }
   if (warp == 0) tmem_alloc<512>(smem_u32(&slot));
   fence_proxy_async_smem();
@@ -77,8 +79,7 @@ __global__ void __launch_bounds__(128, 1) probe(int rows, long long* out) {
       }
       mbar_wait(smem_u32(&bar[15]), par);
       long long t2 = clock64();
-      out[0] = t1 - t0;
-      out[1] = t2 - t0;
+      if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
     }
     __syncwarp();
   }
@@ -87,11 +88,12 @@ __global__ void __launch_bounds__(128, 1) probe(int rows, long long* out) {
   if (warp == 0) { tc_fence_after_sync(); tmem_dealloc<512>(tm); }
 }
 
+static int g_grid = 1;
 template <int VAR>
 void run(long long* d, const char* what) {
   cudaFuncSetAttribute(probe<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  const int rows = 64;
-  probe<VAR><<<1, 128, 200 * 1024>>>(rows, d);
+  const int rows = 512;
+  probe<VAR><<<g_grid, 128, 200 * 1024>>>(rows, d);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("var %d: %s\n", VAR, cudaGetErrorString(e)); exit(1); }
   long long h[2];
@@ -99,9 +101,13 @@ void run(long long* d, const char* what) {
   printf("%-3d %-60s issue %8.1f  total %8.1f clk per row\n", VAR, what, double(h[0]) / rows, double(h[1]) / rows);
 }
 
-int main() {
+int main(int argc, char** argv) {
   long long* d;
   cudaMalloc(&d, 64);
+  g_grid = argc > 1 ? atoi(argv[1]) : 1;
+  const int rnd = argc > 2 ? atoi(argv[2]) : 0;
+  cudaMemcpyToSymbol(g_random, &rnd, sizeof(int));
+  printf("grid %d, %s operand data\n", g_grid, rnd ? "pseudo-random" : "constant");
   run<0>(d, "9 x N=144, fixed D");
   run<1>(d, "9 x N=144, D moves through the 10-block ring");
   run<2>(d, "N=48 overwrite + N=96 + 8 x N=144, ring");

@@ -38,9 +38,10 @@ def main():
         rows = max(s[3], 1)
         print(f'== {mode}: {n}x{h}x{w}, {layers} layers: {us / layers:.1f} us/layer; CTA0 input rows {s[3]}, '
               f'{us * 1e-6 * 1.965e9 / rows:.0f} clk per input row (at 1965 MHz)')
-        print(f'   scheduler   per row: setup {s[0] / rows:6.0f}  tempty-wait {s[4] / rows:6.0f}  full-wait {s[1] / rows:6.0f}  '
-              f'slot-wait+write {s[5] / rows:6.0f}')
-        print(f'   issuer      per row: cmd-wait {s[7] / rows:6.0f}  mma-issue {s[2] / rows:6.0f}  commits {s[6] / rows:6.0f}')
+        print(f'   scheduler   per row: probes+setup {s[0] / rows:6.0f}  barrier-wait {s[4] / rows:6.0f}  slot-wait {s[1] / rows:6.0f}  '
+              f'write+publish {s[5] / rows:6.0f}  rows not staged {s[13] / rows:4.2f}  blocks not drained {s[14] / rows:4.2f}')
+        print(f'   issuer      per row: cmd-wait {s[7] / rows:6.0f}  mma-issue {s[2] / rows:6.0f}  commits {s[6] / rows:6.0f}  '
+              f'polls {s[12] / rows:5.2f}')
         pr = max(s[11], 1)
         print(f'   producer    per row: flag-wait {s[8] / pr:7.0f}  empty-wait {s[9] / pr:7.0f}  issue {s[10] / pr:7.0f}   (rows {s[11]})')
         r0 = max(s[18], 1)
