@@ -25,11 +25,22 @@
 // ready for the next launch (also under CUDA-graph replay, where arguments are frozen).
 //
 // The layer descriptors travel as a kernel parameter (up to 96 x lv_conv_args = 17.7 KB in the constant bank).
+#include <cuda.h>
+
 #include "chain_epilogue.cuh"
 #include "conv_epilogue.cuh"
 #include "lv_common.cuh"
 
+// LV_CHAIN_TMA=0 builds the cp.async halo producers of the first version (two warps, 17 x 16-byte copies per thread and
+// tile) for A/B runs
+#ifndef LV_CHAIN_TMA
+#define LV_CHAIN_TMA 1
+#endif
+
 namespace lv {
+
+// wgrad.cu: cached tensor map with box {px pixels, all chunks, rows rows} over a planar-8 bf16 tensor [n][h][chunks][w][8]
+int activation_tile_map(const void* src, int n, int h, int w, int chunks, int px, int rows, CUtensorMap* out);
 
 extern long long* g_timeline;
 extern int g_use_pdl;
@@ -39,23 +50,38 @@ namespace chain {
 constexpr int kMaxLayers = 96;   // LV_CHAIN_MAX_LAYERS
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2, kHaloPix = kHaloW * kHaloH;  // 10 x 18 = 180
-constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = 64;
+constexpr bool kTmaHalo = LV_CHAIN_TMA != 0;
+constexpr int kEpiWarps = 8, kEpiThreads = kEpiWarps * 32, kProdThreads = kTmaHalo ? 32 : 64;
 constexpr int kMmaWarp = kEpiWarps;
-constexpr int kPubWarp = kMmaWarp + 1 + kProdThreads / 32;    // warp 11: publishes finished tiles
-constexpr int kThreads = kEpiThreads + 32 + kProdThreads + 32;  // 384 = 3 warps per scheduler (<= 168 registers per thread)
+constexpr int kPubWarp = kMmaWarp + 1 + kProdThreads / 32;    // warp 10 (11): publishes finished tiles
+constexpr int kThreads = kEpiThreads + 32 + kProdThreads + 32;  // 352 (384): <= 3 warps per scheduler, 168 registers per thread
 constexpr int kWBufs = 3;
 constexpr uint32_t kWarpsPerTile = 4;                      // epilogue warps per (layer, tile) = done[] increments
 
 struct Params {
   lv_conv_args layer[kMaxLayers];
 };
+// one tensor map per layer: the layer's input, box = one halo tile {10 px, all chunks, 18 rows}; out-of-image pixels
+// (the conv's zero padding) are filled in by the TMA unit
+struct Maps {
+  CUtensorMap src[kMaxLayers];
+};
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
 
 template <int CIN, int NT, int NSTAGE>
 struct Cfg {
   static constexpr int CH = CIN / 8;
   static constexpr int KSTEPS = CIN / 16;
+  // halo tile in shared memory: cp.async build [chunk][row][px] (planes), TMA build [row][chunk][px] (the box order)
   static constexpr int A_PLANE = kHaloPix * 16;
   static constexpr int A_STAGE = CH * A_PLANE;
+  static constexpr int A_ROW = kTmaHalo ? CH * kHaloW * 16 : kHaloW * 16;   // bytes between tile rows of one chunk
+  static constexpr int A_CHUNK = kTmaHalo ? kHaloW * 16 : A_PLANE;          // bytes between 8-channel chunks of one row
   static constexpr int W_TAP = CH * NT * 16;
   static constexpr int W_LAYER = 9 * W_TAP;
   static constexpr int ACC_STRIDE = 64;
@@ -194,8 +220,8 @@ __device__ __forceinline__ uint32_t run_layer(const EpiCtx& cx, const lv_conv_ar
 
 template <int CIN, int NT, int NSTAGE>
 __global__ void __launch_bounds__(kThreads, 1)
-conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const ConvGeom g, uint32_t* __restrict__ done,
-                     const int rot) {
+conv3x3_chain_kernel(const __grid_constant__ Params P, const __grid_constant__ Maps M, const int nlayers, const ConvGeom g,
+                     uint32_t* __restrict__ done, const int rot) {
   using C_ = Cfg<CIN, NT, NSTAGE>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -218,7 +244,7 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(full_bar(s), kProdThreads);
+      mbar_init(full_bar(s), kTmaHalo ? 1 : kProdThreads);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -278,6 +304,43 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
   } else if (warp > kMmaWarp) {
     // =============================== producers: dependency wait + halo tiles -> smem ===============================
     const int ptid = threadIdx.x - (kEpiThreads + 32);
+    const int ddy = lane / 3 - 1, ddx = lane % 3 - 1;   // lanes 0..8 watch the 3x3 tile neighbourhood
+    uint32_t fill = 0;
+    if constexpr (kTmaHalo) {
+      // ONE tensor-map copy per tile (box {10 px, all chunks, 18 rows}, zero fill outside the image) issued by one lane:
+      // against 17 cp.async per thread on two warps it takes ~500-1,000 clk of LSU-path instructions per tile off the
+      // producer, which was the pacing role of small chains (it could not run ahead of the MMAs)
+      pdl_wait();
+      for (int l = 0; l < nlayers; ++l) {
+        for (int tile = first_tile(l); tile < g.total_tiles; tile += G, ++fill) {
+          const int n = tile / tiles_per_img;
+          const int rem = tile - n * tiles_per_img;
+          const int ty = rem / g.tiles_x, tx = rem - ty * g.tiles_x;
+          if (l > 0) {
+            if (lane < 9) {
+              const int yy = ty + ddy, xx = tx + ddx;
+              if (yy >= 0 && yy < g.tiles_y && xx >= 0 && xx < g.tiles_x) {
+                wait_flag(done + tile + ddy * g.tiles_x + ddx, kWarpsPerTile * static_cast<uint32_t>(l));
+              }
+            }
+            __syncwarp();
+          }
+          if (lane == 0) {
+            const int stage = fill % NSTAGE;
+            tl_stamp(g, 0, fill, 0);
+            mbar_wait_relaxed(empty_bar(stage), ((fill / NSTAGE) & 1) ^ 1);
+            tl_stamp(g, 0, fill, 1);
+            // the flags were acquired through the generic proxy; the copy below reads global memory through the async one
+            // (the .global form: 140-500 clk; the unrestricted fence.proxy.async costs ~1,000 clk here)
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            mbar_arrive_expect_tx(full_bar(stage), C_::A_STAGE);
+            tma_load_4d(smem_u32(sA + stage * C_::A_STAGE), &M.src[l], (tx * kTileW - 1) * 8, 0, ty * kTileH - 1, n, full_bar(stage));
+            tl_stamp(g, 0, fill, 2);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
     uint32_t pc_dst[C_::PROD_PIECES];
     int pc_rel[C_::PROD_PIECES], pc_rc[C_::PROD_PIECES];
 #pragma unroll
@@ -289,8 +352,6 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
       pc_rel[i] = ((r * C_::CH + c) * W + col) * 8;
       pc_rc[i] = (idx < kHaloPix * C_::CH) ? ((r << 8) | col) : -1;
     }
-    const int ddy = lane / 3 - 1, ddx = lane % 3 - 1;   // lanes 0..8 watch the 3x3 tile neighbourhood
-    uint32_t fill = 0;
     pdl_wait();
     for (int l = 0; l < nlayers; ++l) {
       const __nv_bfloat16* src_base = reinterpret_cast<const __nv_bfloat16*>(P.layer[l].src[0]);
@@ -330,6 +391,7 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
       }
     }
     cp_async_wait<0>();
+    }
   } else if (warp == kMmaWarp) {
     // =============================== MMA issuer (one elected lane) ================================
     if (elect_one()) {
@@ -344,6 +406,7 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
       };
       load_weights(0);   // packed weights are never written while a launch chain is in flight: no pdl_wait needed
       uint32_t fill = 0;
+      bool next_tempty = false, next_full = false;   // the next job's barriers were seen complete by an early probe
       uint32_t free_pending = 0, free_phase = 0;   // bit b: MMAs reading weight buffer b outstanding / wfree parity
       for (int l = 0; l < nlayers; ++l) {
         const int wb = l % kWBufs;
@@ -363,23 +426,30 @@ conv3x3_chain_kernel(const __grid_constant__ Params P, const int nlayers, const 
           const uint32_t k = fill;
           const uint32_t as = k & 1;
           tl_stamp(g, 1, k, 0);
-          mbar_wait(tempty_bar(as), ((k >> 1) & 1) ^ 1);
-          tc_fence_after_sync();
+          // both barriers of this job were probed while the previous job's last MMAs were being issued (below): when
+          // the pipeline is ahead, neither wait costs a shared-memory round trip here (~190 clk each under MMA load)
+          if (!next_tempty) mbar_wait(tempty_bar(as), ((k >> 1) & 1) ^ 1);
           tl_stamp(g, 1, k, 1);
           const uint32_t d_tmem = tmem_base + as * C_::ACC_STRIDE;
           const int stage = fill % NSTAGE;
-          mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
-          fence_proxy_async_smem();
+          if (!next_full) mbar_wait(full_bar(stage), (fill / NSTAGE) & 1);
+          if (!kTmaHalo) fence_proxy_async_smem();   // cp.async (generic proxy) writes -> UMMA (async proxy) reads
           tc_fence_after_sync();
           tl_stamp(g, 1, k, 2);
           const uint32_t a_addr = smem_u32(sA + stage * C_::A_STAGE);
+          const uint32_t nk = k + 1u, nstage = (fill + 1u) % NSTAGE;
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a_tap = a_addr + ((tap / 3) * kHaloW + (tap % 3)) * 16;
+            const uint32_t a_tap = a_addr + (tap / 3) * C_::A_ROW + (tap % 3) * 16;
             const uint32_t b_tap = sW_addr + tap * C_::W_TAP;
+            if (tap == 7) {
+              // the tensor queue is full from here on: the probes' round trips hide behind the remaining issue stalls
+              next_tempty = mbar_try_wait(tempty_bar(nk & 1u), ((nk >> 1) & 1u) ^ 1u);
+              next_full = mbar_try_wait(full_bar(nstage), ((fill + 1u) / NSTAGE) & 1u);
+            }
 #pragma unroll
             for (int ks = 0; ks < C_::KSTEPS; ++ks) {
-              const uint64_t adesc = umma_smem_desc(a_tap + 2 * ks * C_::A_PLANE, C_::A_PLANE, kHaloW * 16);
+              const uint64_t adesc = umma_smem_desc(a_tap + 2 * ks * C_::A_CHUNK, C_::A_CHUNK, C_::A_ROW);
               const uint64_t bdesc = umma_smem_desc(b_tap + 2 * ks * (NT * 16), NT * 16, 128);
               umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | ks) != 0 ? 1u : 0u);
             }
@@ -512,7 +582,14 @@ int conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, long lon
   }
 #endif
   static thread_local chain::Params params;   // staging only; the launch copies it by value
-  for (int i = 0; i < count; ++i) params.layer[i] = layers[i];
+  static thread_local chain::Maps maps;
+  for (int i = 0; i < count; ++i) {
+    params.layer[i] = layers[i];
+    if (chain::kTmaHalo) {
+      const int rc = activation_tile_map(layers[i].src[0], a0.n, a0.h, a0.w, C_::CH, chain::kHaloW, chain::kHaloH, &maps.src[i]);
+      if (rc != LV_OK) return rc;
+    }
+  }
   auto kern = chain::conv3x3_chain_kernel<48, 48, 4>;
   // once per DEVICE: opt into the dynamic shared memory and make sure one CTA per SM can really be resident -- the
   // data-flow waits need every CTA of the grid running at the same time
@@ -544,7 +621,7 @@ int conv3x3_chain(const lv_conv_args* layers, int count, void* sync_ws, long lon
   attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, params, count, g, static_cast<uint32_t*>(sync_ws), rot));
+  LV_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, params, maps, count, g, static_cast<uint32_t*>(sync_ws), rot));
   count_launch();
   return LV_OK;
 }

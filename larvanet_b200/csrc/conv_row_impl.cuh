@@ -568,7 +568,7 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
           }
           __syncwarp();
           // the rows were written by other CTAs' st.global (generic proxy); the bulk copies read through the async proxy
-          if constexpr (kTmaRows) asm volatile("fence.proxy.async;" ::: "memory");
+          if constexpr (kTmaRows) asm volatile("fence.proxy.async.global;" ::: "memory");   // the unrestricted fence.proxy.async costs ~1,000 clk here
         }
         sp_flag += stat_clk(g) - pc0;      // dependency (flag) wait
         const int ya = max(j.y0 - 1, 0), yb = min(j.y1 + 1, g.H);

@@ -470,7 +470,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 // box {`px` pixels, all chunks, `rows` rows} of a planar-8 bf16 activation tensor [n][h][chunks][w][8]
-static int tile_map(const void* src, int n, int h, int w, int chunks, int px, int rows, CUtensorMap* out) {
+int activation_tile_map(const void* src, int n, int h, int w, int chunks, int px, int rows, CUtensorMap* out) {
   struct Key {
     const void* p; int n, h, w, chunks, px, rows;
     bool operator==(const Key& o) const {
@@ -488,8 +488,8 @@ static int tile_map(const void* src, int n, int h, int w, int chunks, int px, in
   auto it = cache.find(key);
   if (it != cache.end()) { *out = it->second; return LV_OK; }
   EncodeTiledFn enc = encode_fn();
-  LV_CHECK_ARG(enc != nullptr, "wgrad: cuTensorMapEncodeTiled is not available from this driver");
-  LV_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15u) == 0, "wgrad: activation pointers must be 16-byte aligned");
+  LV_CHECK_ARG(enc != nullptr, "tensor map: cuTensorMapEncodeTiled is not available from this driver");
+  LV_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15u) == 0, "tensor map: activation pointers must be 16-byte aligned");
   const cuuint64_t gdim[4] = {static_cast<cuuint64_t>(w) * 8, static_cast<cuuint64_t>(chunks), static_cast<cuuint64_t>(h),
                               static_cast<cuuint64_t>(n)};
   const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(w) * 16, static_cast<cuuint64_t>(w) * 16 * chunks,
@@ -500,7 +500,7 @@ static int tile_map(const void* src, int n, int h, int w, int chunks, int px, in
   const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(src), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  LV_CHECK_ARG(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d x %d-chunk tensor",
+  LV_CHECK_ARG(r == CUDA_SUCCESS, "tensor map: cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d x %d-chunk tensor",
                static_cast<int>(r), n, h, w, chunks);
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, tm);
@@ -534,9 +534,9 @@ int wgrad(const lv_wgrad_item* items_host, const lv_wgrad_item* items_dev, int c
       const lv_wgrad_item& a = items_host[first + k];
       LV_CHECK_ARG(item_tiles(a) < (1ll << 31) / kWMaxItems, "wgrad: item %d has too many tiles", first + k);
       if (item_tiles(a) == 0) continue;
-      rc = tile_map(a.dy, a.n, a.h, a.w, a.cout / 8, kWT_W, kWT_H, &maps.dy[k]);
+      rc = activation_tile_map(a.dy, a.n, a.h, a.w, a.cout / 8, kWT_W, kWT_H, &maps.dy[k]);
       if (rc != LV_OK) return rc;
-      rc = tile_map(a.x, a.n, a.h, a.w, kWCh, kWHaloW, kWHaloH, &maps.x[k]);
+      rc = activation_tile_map(a.x, a.n, a.h, a.w, kWCh, kWHaloW, kWHaloH, &maps.x[k]);
       if (rc != LV_OK) return rc;
     }
     const int G = make_sched(items_host + first, cnt, static_cast<long long>(splits) * cnt, &sc);

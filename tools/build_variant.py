@@ -21,7 +21,7 @@ def main():
     procs = []
     for s in B.SOURCES:
         o = os.path.join(B.BUILD, s.replace('.cu', '.o'))
-        if s.startswith('conv_row'):
+        if s.startswith('conv_row') or s.startswith('conv_chain'):
             o = os.path.join(vdir, f'{name}_{s.replace(".cu", ".o")}')
             procs.append(subprocess.Popen([B._nvcc()] + B.NVCC_FLAGS + defs + ['-c', os.path.join(B.CSRC, s), '-o', o],
                                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
