@@ -19,20 +19,23 @@ long long conv3x3_row_workspace_bytes(int n, int h, int w) {
 }
 
 bool conv3x3_row_supported(const lv_conv_args& a) {
-  return a.dtype == LV_BF16 && a.wlayout == LV_W_KY_STACKED && a.num_src == 1 && a.cin == a.cout && (a.cin == 48 || a.cin == 64) &&
+  if (a.dtype != LV_BF16 || a.wlayout != LV_W_KY_STACKED || a.num_src != 1) return false;
+  // 64 -> (<= 16) with the RGB epilogue: EDSR's last conv (N = 3 * 16 per MMA, 12 MMAs per 128 pixels instead of 36)
+  if (a.cin == 64 && a.cout <= 16) return a.epilogue == LV_EPI_RGB_NCHW;
+  return a.cin == a.cout && (a.cin == 48 || a.cin == 64) &&
          (a.epilogue == LV_EPI_NHWC || (a.epilogue == LV_EPI_PS4_NCHW && a.cout == 48));
 }
 
-// layers[0..count): single-source bf16 C -> C convs (C = 48 or 64, the same for all) with ky-stacked weights on one common
-// (n, h, w); count == 1 needs no workspace.
+// layers[0..count): single-source bf16 C -> C convs (C = 48 or 64, the same for all; or 64 -> <= 16 with the RGB epilogue)
+// with ky-stacked weights on one common (n, h, w); count == 1 needs no workspace.
 int conv3x3_row_chain(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
                       cudaStream_t stream) {
   LV_CHECK_ARG(count >= 1 && count <= row::kMaxLayers, "conv row chain: 1..%d layers per call (got %d)", row::kMaxLayers, count);
   const lv_conv_args& a0 = layers[0];
   for (int i = 0; i < count; ++i) {
     const lv_conv_args& a = layers[i];
-    LV_CHECK_ARG(conv3x3_row_supported(a) && a.cin == a0.cin,
-                 "conv row kernel: layer %d is not a single-source bf16 %d->%d conv with ky-stacked weights", i, a0.cin, a0.cin);
+    LV_CHECK_ARG(conv3x3_row_supported(a) && a.cin == a0.cin && (a.cout <= 16) == (a0.cout <= 16),
+                 "conv row kernel: layer %d is not a single-source bf16 %d->%d conv with ky-stacked weights", i, a0.cin, a0.cout);
     LV_CHECK_ARG(a.n == a0.n && a.h == a0.h && a.w == a0.w, "conv row chain: layer %d has a different geometry", i);
   }
   if (static_cast<long long>(a0.n) * a0.h * a0.w == 0) return LV_OK;

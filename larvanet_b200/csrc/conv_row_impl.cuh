@@ -938,15 +938,21 @@ conv3x3_row_kernel(const __grid_constant__ Params P, const int nlayers, const Ge
         }
       }
       const int first = first_job(l);
-      switch (kind) {
-        case 0: k = run_layer<0, NT, RING>(cx, a, l, first, k); break;
-        case 1: k = run_layer<1, NT, RING>(cx, a, l, first, k); break;
-        case 2: k = run_layer<2, NT, RING>(cx, a, l, first, k); break;
-        case 4: k = run_layer<4, NT, RING>(cx, a, l, first, k); break;
-        case 12: k = run_layer<12, NT, RING>(cx, a, l, first, k); break;
-        case kKindPs4:
-          if constexpr (NT == 48) { k = run_layer<kKindPs4, NT, RING>(cx, a, l, first, k); break; }
-        default: k = run_layer<kKindGeneric, NT, RING>(cx, a, l, first, k); break;
+      if constexpr (NT >= 48) {
+        switch (kind) {
+          case 0: k = run_layer<0, NT, RING>(cx, a, l, first, k); break;
+          case 1: k = run_layer<1, NT, RING>(cx, a, l, first, k); break;
+          case 2: k = run_layer<2, NT, RING>(cx, a, l, first, k); break;
+          case 4: k = run_layer<4, NT, RING>(cx, a, l, first, k); break;
+          case 12: k = run_layer<12, NT, RING>(cx, a, l, first, k); break;
+          case kKindPs4:
+            if constexpr (NT == 48) { k = run_layer<kKindPs4, NT, RING>(cx, a, l, first, k); break; }
+          default: k = run_layer<kKindGeneric, NT, RING>(cx, a, l, first, k); break;
+        }
+      } else {
+        // narrow outputs (EDSR's 64 -> 3 RGB conv, cout padded to 16): the shared 16-channel epilogue routine only
+        (void)kind;
+        k = run_layer<kKindGeneric, NT, RING>(cx, a, l, first, k);
       }
     }
   }
@@ -1063,6 +1069,7 @@ static int launch_row(const lv_conv_args* layers, int count, void* sync_ws, long
 int LV_ROW_ENTRY(const lv_conv_args* layers, int count, void* sync_ws, long long sync_ws_bytes, int max_ctas,
                  cudaStream_t stream) {
   if (layers[0].cin == 48) return launch_row<48, 48, LV_ROW_STAGES48, LV_ROW_WBUFS48>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
+  if (layers[0].cout <= 16) return launch_row<64, 16, 4, 2>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
   return launch_row<64, 64, LV_ROW_STAGES64, 2>(layers, count, sync_ws, sync_ws_bytes, max_ctas, stream);
 }
 

@@ -826,6 +826,14 @@ class EdsrEngine:
                 self._pk[(p, 'ky')] = self._packed_ky[k * step:k * step + nb_]
             self._pack_items += [dict(w=self.arena.views[p + '.weight'], packed=self._pk[(p, 'ky')], transpose=0, i_off=0,
                                       i_cnt=f, cin=f, dtype=act_dtype, wlayout=_lib.LV_W_KY_STACKED) for p in self._body]
+            if f == 64:
+                # the last conv (64 -> 3 at the output resolution) on the row kernel as well: 12 MMAs of N = 48 per 128
+                # pixels instead of 36 of N = 16 on the tile kernel
+                self._pk[('final_conv', 'ky')] = torch.zeros(ops.packed_weight_bytes(3, f, act_dtype), dtype=torch.uint8,
+                                                            device=self.device)
+                self._pack_items.append(dict(w=self.arena.views['final_conv.weight'], packed=self._pk[('final_conv', 'ky')],
+                                             transpose=0, i_off=0, i_cnt=f, cin=f, dtype=act_dtype,
+                                             wlayout=_lib.LV_W_KY_STACKED))
         # (measured at 1 x 270x480: 1.78 ms with the row chain vs 1.93 ms with 33 per-layer launches of the tile kernel)
         self.row_min_pixels = int(os.environ.get('LARVANET_B200_ROW_MIN_PIXELS', str(96 * 1024)))
         self._chain_ws = {}
@@ -897,8 +905,13 @@ class EdsrEngine:
         for s in range(self.nup):
             self._conv(a, f'upsample.body.{2 * s}', 4 * f, out=b.up[s], epilogue=_lib.LV_EPI_PS2_NHWC)
             a = b.up[s]
-        self._conv(a, 'final_conv', 3, epilogue=_lib.LV_EPI_RGB_NCHW, out_hr=b.out,
-                   post_w=v['mean_inverse_shift.weight'], post_b=v['mean_inverse_shift.bias'])
+        if ('final_conv', 'ky') in self._pk and self.use_row_path(*ops.act_dims(a)[:3]) and ops.act_dims(a)[2] >= 129:
+            ops.conv3x3([a], self._pk[('final_conv', 'ky')], 3, bias=v['final_conv.bias'], wlayout=_lib.LV_W_KY_STACKED,
+                        epilogue=_lib.LV_EPI_RGB_NCHW, out_hr=b.out, post_w=v['mean_inverse_shift.weight'],
+                        post_b=v['mean_inverse_shift.bias'])
+        else:
+            self._conv(a, 'final_conv', 3, epilogue=_lib.LV_EPI_RGB_NCHW, out_hr=b.out,
+                       post_w=v['mean_inverse_shift.weight'], post_b=v['mean_inverse_shift.bias'])
 
     def forward(self, x):
         if x.dim() != 4 or x.shape[1] != 3:

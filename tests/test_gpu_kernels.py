@@ -361,6 +361,31 @@ def test_conv64_row_kernel(shape):
     np.testing.assert_allclose(from_nhwc(out3), 0.5 * conv + r1q, rtol=rtol, atol=atol)
 
 
+@pytest.mark.parametrize('shape', [(1, 9, 130), (2, 21, 200), (1, 40, 129), (1, 5, 60)])
+def test_conv64_to_rgb_row_kernel(shape):
+    """EDSR's last conv (64 -> 3, RGB epilogue with the mean-shift 3x3 matrix) on the row-marching kernel (cout padded
+    to 16: N = 48 per MMA, 32-block accumulator ring) against the oracle and against the tile kernel; widths below 129
+    pixels take the cp.async build."""
+    dtype = torch.bfloat16
+    n, h, w = shape
+    rs = np.random.RandomState(6403 + 17 * h + w)
+    wt, b, wq = _rand_conv(rs, 3, 64, dtype, wscale=0.04)
+    x, xq = _act(rs, n, 64, h, w, dtype)
+    post_w = rs.uniform(-1, 1, (3, 3)).astype(np.float32)
+    post_b = rs.uniform(-1, 1, 3).astype(np.float32)
+    bt = torch.from_numpy(b).cuda()
+    pw, pb = torch.from_numpy(post_w).cuda(), torch.from_numpy(post_b).cuda()
+    conv = O.conv2d(xq, wq, b.astype(np.float64))                       # [n, 3, h, w]
+    want = np.einsum('dc,nchw->ndhw', post_w.astype(np.float64), conv) + post_b.astype(np.float64)[None, :, None, None]
+    out = torch.full((n, 3, h, w), -7.0, dtype=torch.float32, device='cuda')
+    ops.conv3x3([x], _pack(wt, dtype, 64, wlayout=_lib.LV_W_KY_STACKED), 3, bias=bt, epilogue=_lib.LV_EPI_RGB_NCHW,
+                out_hr=out, post_w=pw, post_b=pb, wlayout=_lib.LV_W_KY_STACKED)
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=2e-5, atol=2e-3)
+    ref = torch.empty_like(out)
+    ops.conv3x3([x], _pack(wt, dtype, 64), 3, bias=bt, epilogue=_lib.LV_EPI_RGB_NCHW, out_hr=ref, post_w=pw, post_b=pb)
+    assert (out - ref).abs().max().item() <= 2e-3     # same products, different fp32 summation order
+
+
 @pytest.mark.parametrize('shape', [(1, 270, 480), (8, 64, 64), (16, 48, 48), (1, 1, 1), (1, 2, 127), (1, 129, 128), (2, 11, 128)])
 def test_row_kernel_equals_tap_major_kernel_at_size(shape):
     """Row-marching kernel vs the tap-major tensor-core kernel on identical operands at BASELINE frame / batch sizes and
