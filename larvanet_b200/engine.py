@@ -198,8 +198,6 @@ class LarvaEngine:
         cap = int(os.environ.get('LARVANET_B200_SHAPE_CACHE', '4'))
         self._infer = _ShapeCache(cap)   # (n, h, w, exit_leg) -> buffers + graph, LRU-bounded
         self._train = _ShapeCache(2)
-        self._overlap_head = os.environ.get('LARVANET_B200_OVERLAP_HEAD', '1') != '0'
-        self._side_stream = None
         self.simt = False  # tests flip this to cross-check the tensor-core kernels on CUDA cores
         # consecutive 48->48 convs run as ONE persistent data-flow launch (ops.conv3x3_chain); LARVANET_B200_CHAIN=0
         # falls back to one launch per conv
@@ -614,27 +612,13 @@ class LarvaEngine:
                 self._dgrad(b.dt[i][j], pj + '.0', out=dst, res1=b.da[i][j], res2=dfout if j == 0 else None)
             dnext = b.dfin[i]
         self._flush_chain(end=True)
-        # The head conv's weight gradient (two small launches, ~18 us, latency-bound) runs on a side stream next to the
-        # persistent weight-gradient kernel of the 48 -> 48 layers, which leaves half of every SM's shared memory and most
-        # of its thread slots free; both only READ what the backward chain wrote.  Fork / join by events: the same
-        # calls are a fork / join inside a CUDA-graph capture.  LARVANET_B200_OVERLAP_HEAD=0: one stream.
-        head = lambda: ops.head_wgrad(b.x, b.dfin[0], self.arena.grad_views['head.feature_extraction.weight'],
-                                      self.arena.grad_views['head.feature_extraction.bias'], scale,
-                                      overwrite=not (self.simt or self.act_dtype != torch.bfloat16), workspace=b.head_ws)
-        if self._overlap_head:
-            cur = torch.cuda.current_stream()
-            if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream(device=self.device)
-            self._side_stream.wait_stream(cur)
-            with torch.cuda.stream(self._side_stream):
-                head()
-            for wb in b.wgrad:
-                wb.launch(simt=self.simt)
-            cur.wait_stream(self._side_stream)
-        else:
-            for wb in b.wgrad:
-                wb.launch(simt=self.simt)
-            head()
+        # (tried: the head conv's weight gradient on a side stream next to the persistent weight-gradient kernel -- the
+        # step got SLOWER, 0.608 vs 0.517 ms: the small kernel's blocks delay the persistent kernel's one-CTA-per-SM wave)
+        for wb in b.wgrad:
+            wb.launch(simt=self.simt)
+        ops.head_wgrad(b.x, b.dfin[0], self.arena.grad_views['head.feature_extraction.weight'],
+                       self.arena.grad_views['head.feature_extraction.bias'], scale,
+                       overwrite=not (self.simt or self.act_dtype != torch.bfloat16), workspace=b.head_ws)
 
     def train_step(self, x, truth, keep_exits=False):
         """One forward+backward.  Leaves d(loss)/d(param) in the gradient arena (== every param.grad) and returns the
