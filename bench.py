@@ -341,7 +341,7 @@ def run_ours(a):
             yield host_pool[i % POOL]
             i += 1
 
-    feeder = DevicePrefetcher(host_batches(), dev, depth=2)
+    feeder = DevicePrefetcher(host_batches(), dev, depth=2, defer=True)
 
     def step_e2e(i):
         x, t = next(feeder)

@@ -194,6 +194,7 @@ class LarvaEngine:
         self._head_grad_slice = self.arena.slice_of('head.')
         self._alloc_packed()
         self._packed_version = None
+        self._seen_version = None
         self._packed_bwd = False
         cap = int(os.environ.get('LARVANET_B200_SHAPE_CACHE', '4'))
         self._infer = _ShapeCache(cap)   # (n, h, w, exit_leg) -> buffers + graph, LRU-bounded
@@ -283,11 +284,12 @@ class LarvaEngine:
 
     def repack(self, backward=False, force=False):
         """Refresh the packed bf16/fp32 conv operands from the fp32 master weights when they changed."""
+        ver = self._seen_version = self.arena.version()     # one walk over the parameters per step (~15 us of host time)
         if not force and self._packed_version is not None:
-            if self.arena.version() == self._packed_version and (self._packed_bwd or not backward):
+            if ver == self._packed_version and (self._packed_bwd or not backward):
                 return
         ops.pack_weights_prebuilt(self._pack_arr_all if backward else self._pack_arr_fwd)   # launch first, book-keep after
-        self._packed_version = self.arena.version()
+        self._packed_version = ver
         self._packed_bwd = backward
 
     def repack_ky(self, backward=False):
@@ -319,8 +321,10 @@ class LarvaEngine:
         return self._fused_convs is not None and not self.simt
 
     def weights_updated_and_packed(self):
-        """Called by FusedAdamW after lv_adamw_pack_step: both operand forms are current."""
-        self._packed_version = self.arena.version()
+        """Called by FusedAdamW after lv_adamw_pack_step: both operand forms are current.  The kernel updates the arena
+        through raw pointers (no tensor version changes), so the version seen by this step's `repack` still stands; a
+        parameter modified in place between train_step() and optim.step() only costs one extra re-pack next step."""
+        self._packed_version = self._seen_version if self._seen_version is not None else self.arena.version()
         self._packed_bwd = True
 
     def weights_updated(self):

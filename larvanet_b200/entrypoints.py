@@ -338,7 +338,7 @@ def train_main(argv=None, epoch_bookkeeping=False):
     if getattr(dataloader, 'device', None) is not None and getattr(dataloader, 'device').type == 'cuda':
         feeder = host_batches()   # GPU-resident loader (device-side crop / rot90 / flip): batches are born on the device
     else:
-        feeder = DevicePrefetcher(host_batches(), model.device, depth=2)
+        feeder = DevicePrefetcher(host_batches(), model.device, depth=2, defer=True)
     try:
         while model.global_step < args.max_steps:
             scale = model.get_next_train_scale()

@@ -25,7 +25,13 @@ def dtype_id(dt):
         raise _lib.LarvaNetB200Error(f'unsupported activation dtype {dt}; use torch.bfloat16 or torch.float32') from None
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream():
+    # the raw-handle query is ~10x cheaper than building a torch.cuda.Stream object (this runs on every launch)
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

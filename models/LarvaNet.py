@@ -18,6 +18,7 @@ import torch.nn as nn
 import torch.optim as optim
 
 from models.base import BaseModel
+from larvanet_b200.prefetch import run_deferred as _run_deferred_refills
 
 NUM_FILTERS = 48  # reference models/LarvaNet.py:226,239,254
 
@@ -273,6 +274,7 @@ class LarvaNet(BaseModel):
         # forward of every exit + L1 losses + full backward in one fused pass; gradients land in param.grad
         loss = eng.train_step(input_tensor, truth_tensor)
         self.optim.step()
+        _run_deferred_refills()     # host-side input prefetch work, now that the GPU is busy (larvanet_b200/prefetch.py)
 
         if self.global_step == 1:
             self.validate_for_train(args, val_dataloader)

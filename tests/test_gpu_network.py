@@ -360,6 +360,19 @@ def test_device_prefetcher_feeds_identical_batches():
     assert len(got) == len(host)
     for (x, t), (hx, ht) in zip(got, host):
         assert torch.equal(x.cpu(), hx) and torch.equal(t.cpu(), ht)
+    # postponed refills (defer=True): issued by run_deferred() after the consumer enqueued its work, or caught up by the
+    # next __next__ when nobody calls it -- same batches, same order, nothing dropped at the end
+    from larvanet_b200 import prefetch
+    for call_hook in (True, False):
+        got = []
+        for x, t in DevicePrefetcher(iter(host), 'cuda', depth=2, defer=True):
+            got.append((x.clone(), t.clone()))
+            torch.cuda._sleep(200000)
+            if call_hook:
+                prefetch.run_deferred()
+        assert len(got) == len(host)
+        for (x, t), (hx, ht) in zip(got, host):
+            assert torch.equal(x.cpu(), hx) and torch.equal(t.cpu(), ht)
 
 
 def test_fused_adamw_pack_equals_separate_kernels(golden_dir):
