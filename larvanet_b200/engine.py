@@ -631,7 +631,6 @@ class LarvaEngine:
         n, _, h, w = (int(v) for v in x.shape)
         if tuple(truth.shape) != (n, 3, 4 * h, 4 * w):
             raise LarvaNetB200Error(f'truth shape {tuple(truth.shape)} does not match 4x input {tuple(x.shape)}')
-        self.repack(backward=True)
         key = (n, h, w, bool(keep_exits))
 
         def build():
@@ -655,10 +654,11 @@ class LarvaEngine:
 
         ent = self._train.get(key, build)
         b = ent['bufs']
+        b.x.copy_(x, non_blocking=True)          # the GPU starts on the input copies while the host checks the weights
+        b.truth.copy_(truth, non_blocking=True)
+        self.repack(backward=True)
         if b.row:
             self.repack_ky(backward=True)
-        b.x.copy_(x, non_blocking=True)
-        b.truth.copy_(truth, non_blocking=True)
         _run_cached(self, ent, lambda: self._run_train(b))
         self.arena.attach_grads()   # host-only book-keeping, after the launches so that the GPU is already busy
         self.last_exits = b.exits
