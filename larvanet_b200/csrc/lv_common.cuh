@@ -253,10 +253,16 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+#ifndef LV_RELAXED_SLEEP_NS
+#define LV_RELAXED_SLEEP_NS 128
+#endif
+#ifndef LV_RELAXED_HINT_NS
+#define LV_RELAXED_HINT_NS 400
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait_hint(bar, parity, 400u)) {
-    __nanosleep(128);   // back off: eight spinning epilogue warps otherwise issue a third of the SM's instructions
+  while (!mbar_try_wait_hint(bar, parity, LV_RELAXED_HINT_NS)) {
+    if (LV_RELAXED_SLEEP_NS > 0) __nanosleep(LV_RELAXED_SLEEP_NS);   // back off: eight spinning epilogue warps otherwise issue a third of the SM's instructions
     if (++spins > LV_SPIN_LIMIT) asm volatile("trap;");
   }
 }
