@@ -11,7 +11,8 @@
 //     dedicated publisher warp turns "all 4 warps arrived" into one red.release.gpu, which is what waits for the SM's
 //     store acknowledgements (1.1-1.5k clk);
 //   * the job (layer l, tile X) may start when all 9 tiles around X have finished every earlier layer (done >= 4*l;
-//     every halo producer warp polls with relaxed loads and finishes with one ld.acquire.gpu).  That one rule covers the
+//     the halo producer warp polls with relaxed loads and finishes with one ld.acquire.gpu, then fetches the 18x10 halo
+//     tile with ONE tensor-map TMA copy whose out-of-bounds fill is the conv's zero padding).  That one rule covers the
 //     halo reads, the same-tile residual / mask reads of the epilogue, and the write-after-read hazards of ping-pong
 //     activation buffers;
 //   * the halo / MMA / epilogue pipeline never drains between layers: the producers run ahead into layer l+1 while
