@@ -20,19 +20,15 @@ __device__ __forceinline__ void cubic_coeffs(float t, float* c) {
   c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
-// Threads = 256 pixels x G channel groups (G = min(cout / 16, 4)): group g computes output channels 16g..16g+15 (+ 64, ...)
-// of its pixel and colour plane g of the bicubic base.  One thread per pixel for everything left one block of 8 warps per
-// SM grinding through ~2,000 dependent instructions (13.6 us for 16 x 48x48 patches, 19 us for a 320x180 frame).
 template <typename T>
-__global__ void __launch_bounds__(kHT* kHT * 4)
+__global__ void __launch_bounds__(kHT* kHT)
 head_bicubic_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                     const float* __restrict__ pre_w, const float* __restrict__ pre_b, T* __restrict__ fea,
                     float* __restrict__ base_hr, int N, int H, int W, int cout) {
   __shared__ float sx[3][kHH][kHH + 1];   // index-clamped LR tile (what bicubic reads)
   __shared__ float sc[3][kHT + 2][kHT + 3];  // conv input: optional 1x1 pre-conv, ZERO outside the image
   extern __shared__ float sw[];           // [27][cout] transposed weights, then [cout] bias
-  const int pix = threadIdx.x % (kHT * kHT), grp = threadIdx.x / (kHT * kHT), ngrp = blockDim.x / (kHT * kHT);
-  const int tx = pix % kHT, ty = pix / kHT;
+  const int tx = threadIdx.x % kHT, ty = threadIdx.x / kHT;
   const int x0 = blockIdx.x * kHT, y0 = blockIdx.y * kHT, n = blockIdx.z;
 
   for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
@@ -74,7 +70,7 @@ head_bicubic_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) in[c * 9 + ky * 3 + kx] = sc[c][ty + ky][tx + kx];
-  for (int co0 = grp * 16; co0 < cout; co0 += 16 * ngrp) {
+  for (int co0 = 0; co0 < cout; co0 += 16) {
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = sw[27 * cout + co0 + i];
@@ -94,7 +90,8 @@ head_bicubic_kernel(const float* __restrict__ x, const float* __restrict__ w, co
 #pragma unroll
   for (int i = 0; i < 4; ++i) cubic_coeffs(tph[i], cw[i]);
   const size_t W4 = static_cast<size_t>(W) * 4, H4 = static_cast<size_t>(H) * 4;
-  for (int c = grp; c < 3; c += ngrp) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
     // horizontal pass on the 5 LR rows y-2..y+2 -> hz[row][j]
     float hz[5][4];
 #pragma unroll
@@ -268,12 +265,11 @@ int head_bicubic_fwd(const float* x, const float* w, const float* b, const float
   LV_CHECK_ARG(n <= 65535, "head conv: batch too large for one launch");
   dim3 grid((w_ + kHT - 1) / kHT, (h + kHT - 1) / kHT, n);
   const size_t smem = static_cast<size_t>(28) * cout * sizeof(float);
-  const int groups = cout / 16 < 4 ? cout / 16 : 4;
   if (dtype == LV_F32)
-    head_bicubic_kernel<float><<<grid, kHT * kHT * groups, smem, stream>>>(x, w, b, pre_w, pre_b, static_cast<float*>(fea),
-                                                                          base_hr, n, h, w_, cout);
+    head_bicubic_kernel<float><<<grid, kHT * kHT, smem, stream>>>(x, w, b, pre_w, pre_b, static_cast<float*>(fea), base_hr,
+                                                                 n, h, w_, cout);
   else
-    head_bicubic_kernel<__nv_bfloat16><<<grid, kHT * kHT * groups, smem, stream>>>(
+    head_bicubic_kernel<__nv_bfloat16><<<grid, kHT * kHT, smem, stream>>>(
         x, w, b, pre_w, pre_b, static_cast<__nv_bfloat16*>(fea), base_hr, n, h, w_, cout);
   LV_LAUNCH_OK();
   return LV_OK;
