@@ -244,3 +244,61 @@ def test_leg_plugins_share_the_state_dict_and_validate_leg(modname, v2):
     bad.parse_args(['--num_modules=2', '--num_blocks=1,1', '--leg=3'])
     with pytest.raises(ValueError):
         bad.prepare(is_training=False, scales=[4])
+
+
+@pytest.mark.parametrize('defer,call_hook', [(False, False), (True, True), (True, False)])
+def test_prefetcher_control_flow_without_a_gpu(monkeypatch, defer, call_hook):
+    """DevicePrefetcher's slot / refill book-keeping with the CUDA stream and event objects replaced by recorders (the
+    copies themselves are plain CPU copies here): every batch comes out once, in order, nothing is dropped at the end,
+    a slot is only refilled after the consumer's "done with it" event was recorded, and with defer=True the refill
+    happens in run_deferred() -- or at the next __next__ when nobody calls it."""
+    import contextlib
+    from larvanet_b200 import prefetch
+
+    log = []
+
+    class FakeEvent:
+        def record(self, stream=None):
+            log.append(('record', id(self)))
+
+    class FakeStream:
+        def __init__(self, device=None):
+            pass
+
+        def wait_event(self, ev):
+            log.append(('wait', id(ev)))
+
+    monkeypatch.setattr(torch.cuda, 'Stream', FakeStream)
+    monkeypatch.setattr(torch.cuda, 'Event', FakeEvent)
+    monkeypatch.setattr(torch.cuda, 'stream', lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda device=None: FakeStream())
+    host = [(torch.full((2, 3), float(i)), torch.full((2, 5), float(-i))) for i in range(7)]
+    issued = []
+    real_issue = prefetch.DevicePrefetcher._issue
+
+    def counting_issue(self):
+        issued.append(len(got))
+        real_issue(self)
+
+    monkeypatch.setattr(prefetch.DevicePrefetcher, '_issue', counting_issue)
+    got = []
+    feeder = prefetch.DevicePrefetcher(iter(host), 'cpu', depth=2, defer=defer)
+    assert issued == [0, 0]                      # two batches in flight before the first hand-out
+    for x, t in feeder:
+        got.append((x.clone(), t.clone()))
+        if defer and call_hook:
+            before = len(issued)
+            prefetch.run_deferred()
+            assert len(issued) - before == (1 if len(got) >= 2 else 0)    # the refill owed by this hand-out, now
+            prefetch.run_deferred()
+            assert len(issued) - before == (1 if len(got) >= 2 else 0)    # and only once
+    assert len(got) == len(host)
+    for (x, t), (hx, ht) in zip(got, host):
+        assert torch.equal(x, hx) and torch.equal(t, ht)
+    # a refill of a slot is always preceded by the consumer's event for that slot having been recorded
+    recorded = set()
+    for kind, ev in log:
+        if kind == 'record':
+            recorded.add(ev)
+        else:
+            assert ev in recorded
