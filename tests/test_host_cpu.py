@@ -302,3 +302,42 @@ def test_prefetcher_control_flow_without_a_gpu(monkeypatch, defer, call_hook):
             recorded.add(ev)
         else:
             assert ev in recorded
+
+
+def test_band_ranges_cover_the_frame_with_the_receptive_halo():
+    """tiling.band_ranges / receptive_halo (exact band-sharded inference): bands partition the rows, read ranges add the
+    halo clipped at the frame, the halo equals the number of 3x3 conv rings on the longest path + the bicubic margin."""
+    from larvanet_b200 import tiling
+    assert tiling.receptive_halo([4, 4, 4, 4]) == 1 + 2 * 16 + 2 + 2           # head + 32 body convs + 2 leg convs + bicubic
+    assert tiling.receptive_halo([4, 4, 4, 4], v2=True) == 1 + 32 + 3 + 2        # V2 tail: merge conv + 2
+    assert tiling.receptive_halo([4, 4, 4, 4], exit_leg=1) == 1 + 8 + 2 + 2
+    assert tiling.receptive_halo([4, 4], exit_leg=0) == 2                        # bicubic base only
+    for height, bands, halo in [(270, 4, 37), (10, 3, 37), (7, 16, 2), (1, 1, 5)]:
+        r = tiling.band_ranges(height, bands, halo)
+        assert len(r) == min(bands, height)
+        assert r[0][0] == 0 and r[-1][1] == height
+        for (y0, y1, lo, hi), nxt in zip(r, r[1:] + [None]):
+            assert y0 < y1 and lo == max(0, y0 - halo) and hi == min(height, y1 + halo)
+            if nxt is not None:
+                assert nxt[0] == y1
+    assert tiling.bands_for_rank(7, 1, 3) == [1, 4]
+
+
+def test_shape_cache_is_lru_bounded():
+    """engine._ShapeCache (unbounded per-shape buffers + graphs): at most `capacity` entries, least
+    recently used evicted first, hit counts drive the capture-on-second-use policy."""
+    from larvanet_b200.engine import _ShapeCache
+    built = []
+    c = _ShapeCache(2)
+    mk = lambda k: (lambda: built.append(k) or object())
+    e1 = c.get('a', mk('a'))
+    assert e1['hits'] == 1 and e1['graph'] is None
+    assert c.get('a', mk('a')) is e1 and e1['hits'] == 2 and built == ['a']
+    c.get('b', mk('b'))
+    c.get('a', mk('a'))            # 'a' is now the most recent
+    c.get('c', mk('c'))            # evicts 'b'
+    assert len(c) == 2 and built == ['a', 'b', 'c']
+    c.get('b', mk('b'))            # rebuilt: it was evicted
+    assert built == ['a', 'b', 'c', 'b'] and len(c) == 2
+    c.clear()
+    assert len(c) == 0
