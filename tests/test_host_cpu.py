@@ -341,3 +341,22 @@ def test_shape_cache_is_lru_bounded():
     assert built == ['a', 'b', 'c', 'b'] and len(c) == 2
     c.clear()
     assert len(c) == 0
+
+
+def test_fused_adamw_is_a_plain_adamw_to_torch_without_the_profiler_wrapper():
+    """FusedAdamW keeps the torch.optim.AdamW surface (param_groups, schedulers, state_dict) and declines the per-class
+    profiler wrapper torch puts around Optimizer.step (host time per step); without an attached engine step() fails
+    loudly -- there is no unfused fallback."""
+    from larvanet_b200.optim import FusedAdamW
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = FusedAdamW([p], lr=4e-4)
+    assert isinstance(opt, torch.optim.AdamW) and opt.param_groups[0]['lr'] == 4e-4
+    assert getattr(FusedAdamW.step, 'hooked', False) and not hasattr(FusedAdamW.step, '__wrapped__')
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, mode='max', factor=0.5, patience=0, threshold=0.0)
+    sched.step(1.0)
+    sched.step(0.5)
+    sched.step(0.4)
+    assert opt.param_groups[0]['lr'] < 4e-4                 # the scheduler drives our param group
+    with pytest.raises(_lib.LarvaNetB200Error):
+        opt.step()
+    assert 'param_groups' in opt.state_dict()
