@@ -1,4 +1,4 @@
-"""Diagnostic: per-parameter gradient error of the fused train step vs the oracle (same-sign backward)."""
+"""Diagnostic (test infrastructure, run by hand: python tests/grad_table.py [bf16|fp32]): per-parameter gradient error of the fused train step vs the oracle (same-sign backward)."""
 import importlib, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
